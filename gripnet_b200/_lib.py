@@ -1,0 +1,104 @@
+"""ctypes binding of ``libgripnet_b200.so`` (the C ABI of ``include/gripnet_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded
+the import of any compute module fails loudly (``GripnetLibraryError``).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgripnet_b200.so")
+
+
+class GripnetLibraryError(RuntimeError):
+    pass
+
+
+class GnCsr(C.Structure):
+    """Mirror of ``gn_csr`` (include/gripnet_b200.h)."""
+    _fields_ = [
+        ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int32), ("chunk_len", C.c_int32),
+        ("n_chunks", C.c_int32), ("_pad", C.c_int32),
+        ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
+        ("chunk_ptr", C.c_void_p), ("chunk_row", C.c_void_p), ("chunk_beg", C.c_void_p),
+        ("row_counter", C.c_void_p),
+    ]
+
+
+_P, _I32, _I64, _F, _SZ, _INT = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_int
+_CSR = C.POINTER(GnCsr)
+
+# name -> (restype, argtypes); every symbol declared in include/gripnet_b200.h
+SIGNATURES = {
+    "gn_version": (_INT, []),
+    "gn_error_string": (C.c_char_p, [_INT]),
+    "gn_launch_count": (C.c_uint64, []),
+    "gn_csr_from_keys_workspace_bytes": (_SZ, [_I64, _I32]),
+    "gn_csr_from_keys": (_INT, [_P, _I64, _I32, _P, _P, _P, _SZ, _P]),
+    "gn_build_chunks_workspace_bytes": (_SZ, [_I32]),
+    "gn_build_chunks": (_INT, [_P, _I32, _I32, _P, _P, _P, _I64, _P, _SZ, _P]),
+    "gn_gcn_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "gn_gcn_prep": (_INT, [_P, _P, _P, _I64, _I32, _I32, _INT, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                           _P, _P, _P, _P, _SZ, _P]),
+    "gn_rgcn_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "gn_rgcn_prep": (_INT, [_P, _P, _I64, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gn_edge_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
+    "gn_edge_prep": (_INT, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gn_index_prep_workspace_bytes": (_SZ, [_I64, _I32]),
+    "gn_index_prep": (_INT, [_P, _I64, _I32, _P, _P, _P, _SZ, _P]),
+    "gn_spmm": (_INT, [_CSR, _P, _I64, _I32, _P, _P, _P, _I64, _INT, _P, _I64, _P, _P]),
+    "gn_sgemm": (_INT, [_INT, _INT, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _I32, _I64, _I64, _I64, _INT,
+                        _F, _INT, _P, _I64, _P, _I64, _P, _I32, _P, _SZ, _P]),
+    "gn_distmult_fwd": (_INT, [_P, _I64, _I32, _P, _P, _P, _P, _I64, _INT, _P, _P]),
+    "gn_distmult_coef": (_INT, [_P, _P, _I64, _INT, _P, _P]),
+    "gn_distmult_bwd_z": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I64, _P, _P]),
+    "gn_distmult_bwd_w": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "gn_softmax_fwd": (_INT, [_P, _I64, _I32, _P, _P]),
+    "gn_softmax_bwd": (_INT, [_P, _P, _I64, _I32, _P, _P]),
+    "gn_map2d": (_INT, [_INT, _P, _I64, _P, _I64, _I64, _I32, _P]),
+    "gn_relu_bwd": (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
+    "gn_abs_bwd": (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _F, _P]),
+    "gn_axpby": (_INT, [_P, _I64, _F, _P, _I64, _F, _P, _I64, _I64, _I32, _P]),
+    "gn_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
+    "gn_colsum": (_INT, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
+    "gn_loss_workspace_bytes": (_SZ, [_I64]),
+    "gn_lp_loss_fwd": (_INT, [_P, _I64, _P, _I64, _F, _P, _P, _SZ, _P]),
+    "gn_lp_loss_bwd": (_INT, [_P, _I64, _P, _I64, _F, _P, _P, _P, _P]),
+    "gn_nc_loss_fwd": (_INT, [_P, _I64, _I32, _P, _F, _P, _P, _SZ, _P]),
+    "gn_nc_loss_bwd": (_INT, [_P, _I64, _I32, _P, _F, _P, _P, _P]),
+}
+
+EW_COPY, EW_ABS, EW_RELU, EW_ADD = 0, 1, 2, 3
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise GripnetLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m gripnet_b200.build` "
+            "(nvcc, sm_100a).  gripnet_b200 has no CPU or PyTorch fallback.")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise GripnetLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = load().gn_error_string(status).decode()
+        raise RuntimeError(f"gripnet_b200: {what or 'call'} failed: {msg} (status {status})")
+
+
+def launch_count():
+    return int(load().gn_launch_count())

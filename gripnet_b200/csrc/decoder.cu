@@ -1,0 +1,274 @@
+// K9/K10/K11: DistMult link decoder (fused gather-multiply-reduce), its
+// deterministic backward, and the softmax pieces of the multi-class decoder.
+// Reference arithmetic restated: gripnet/decoder.py:19-23, :38-45.
+#include "rowsplit.cuh"
+
+namespace gn {
+
+constexpr int kMaxNV = 8;  // vectors per feature lane
+
+// ---------------------------------------------------------------------------
+// forward: one edge per group of LPE lanes; nothing of size [E,D] is materialised
+// ---------------------------------------------------------------------------
+template <int LPE, int VEC>
+__global__ void __launch_bounds__(256) distmult_fwd_kernel(const float* __restrict__ z, int64_t ldz, int D,
+                                                           const float* __restrict__ w,
+                                                           const int64_t* __restrict__ src,
+                                                           const int64_t* __restrict__ dst,
+                                                           const int64_t* __restrict__ etype, int64_t n_edges,
+                                                           int sigmoid, float* __restrict__ out) {
+  constexpr int EPI = 32 / LPE;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / LPE, fl = lane % LPE;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t e0 = warp * EPI; e0 < n_edges; e0 += n_warps * EPI) {
+    const int64_t e = e0 + slot;
+    float s = 0.f;
+    if (e < n_edges) {
+      const float* za = z + src[e] * ldz;
+      const float* zb = z + dst[e] * ldz;
+      const float* wr = w + etype[e] * int64_t(D);
+      for (int f = fl * VEC; f < D; f += LPE * VEC) {
+        const Vec<VEC> a = load_vec<VEC>(za + f), b = load_vec<VEC>(zb + f), c = load_vec<VEC>(wr + f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) s = fmaf(a.v[i] * b.v[i], c.v[i], s);
+      }
+    }
+#pragma unroll
+    for (int o = LPE / 2; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+    if (e < n_edges && fl == 0) out[e] = sigmoid ? 1.0f / (1.0f + expf(-s)) : s;
+  }
+}
+
+__global__ void distmult_coef_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, int64_t n,
+                                     int sigmoid, float* __restrict__ coef) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float g = grad_out[e];
+  if (sigmoid) {
+    const float s = out[e];
+    g *= s * (1.0f - s);
+  }
+  coef[e] = g;
+}
+
+// ---------------------------------------------------------------------------
+// backward: row-split segmented reductions (no atomics on data)
+//   MODE 0: rows = nodes,     entry (other, rel, e): coef[e] * z[other] .* w[rel]
+//   MODE 1: rows = relations, entry e:               coef[e] * z[src_e] .* z[dst_e]
+// ---------------------------------------------------------------------------
+template <int LPE, int VEC, int MODE>
+__global__ void __launch_bounds__(256) distmult_bwd_kernel(const gn_csr csr, const int32_t* __restrict__ ent_a,
+                                                           const int32_t* __restrict__ ent_b,
+                                                           const int32_t* __restrict__ ent_eid,
+                                                           const int64_t* __restrict__ src,
+                                                           const int64_t* __restrict__ dst,
+                                                           const float* __restrict__ coef, const float* __restrict__ z,
+                                                           int64_t ldz, int D, const float* __restrict__ w,
+                                                           float* __restrict__ outp, int64_t ldo,
+                                                           float* __restrict__ partial) {
+  ChunkInfo ci;
+  if (!chunk_info(csr, ci)) return;
+  constexpr int EPI = 32 / LPE;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / LPE, fl = lane % LPE;
+
+  Vec<VEC> acc[kMaxNV];
+#pragma unroll
+  for (int v = 0; v < kMaxNV; ++v)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[v].v[i] = 0.f;
+
+  for (int base = ci.beg; base < ci.end; base += EPI) {
+    const int s = base + slot;
+    if (s < ci.end) {
+      const float* pa;
+      const float* pb;
+      float g;
+      if (MODE == 0) {
+        const int e = __ldg(ent_eid + s);
+        g = __ldg(coef + e);
+        pa = z + int64_t(__ldg(ent_a + s)) * ldz;
+        pb = w + int64_t(__ldg(ent_b + s)) * D;
+      } else {
+        const int e = __ldg(ent_eid + s);
+        g = __ldg(coef + e);
+        pa = z + src[e] * ldz;
+        pb = z + dst[e] * ldz;
+      }
+#pragma unroll
+      for (int v = 0; v < kMaxNV; ++v) {
+        const int f = (v * LPE + fl) * VEC;
+        if (f < D) {
+          const Vec<VEC> a = load_vec<VEC>(pa + f), b = load_vec<VEC>(pb + f);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[v].v[i] = fmaf(g * a.v[i], b.v[i], acc[v].v[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < kMaxNV; ++v) reduce_slots<LPE, VEC>(acc[v]);
+
+  const int row = ci.row;
+  auto emit = [&](int, int f, const Vec<VEC>& sum) { store_vec<VEC>(outp + int64_t(row) * ldo + f, sum); };
+  finish_row<LPE, VEC, kMaxNV>(csr, ci, acc, D, partial, emit);
+}
+
+// ---------------------------------------------------------------------------
+// softmax (warp per row)
+// ---------------------------------------------------------------------------
+__global__ void softmax_fwd_kernel(const float* __restrict__ x, int64_t n, int C, float* __restrict__ y) {
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + row * C;
+  float m = -INFINITY;
+  for (int c = lane; c < C; c += 32) m = fmaxf(m, xr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += expf(xr[c] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+  const float inv = 1.0f / s;
+  for (int c = lane; c < C; c += 32) y[row * C + c] = expf(xr[c] - m) * inv;
+}
+
+__global__ void softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gy, int64_t n, int C,
+                                   float* __restrict__ gx) {
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float dot = 0.f;
+  for (int c = lane; c < C; c += 32) dot = fmaf(y[row * C + c], gy[row * C + c], dot);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(kFull, dot, o);
+  for (int c = lane; c < C; c += 32) gx[row * C + c] = y[row * C + c] * (gy[row * C + c] - dot);
+}
+
+struct WidthPlan {
+  int vec, lpe;
+  bool ok;
+};
+
+// lanes-per-entry for a D-wide row with at most kMaxNV vectors per lane
+inline WidthPlan plan_width(int D, bool can_vec4) {
+  WidthPlan p{can_vec4 ? 4 : 1, 0, true};
+  const int units = (D + p.vec - 1) / p.vec;
+  if (units <= 4 * kMaxNV) p.lpe = 4;
+  else if (units <= 8 * kMaxNV) p.lpe = 8;
+  else if (units <= 32 * kMaxNV) p.lpe = 32;
+  else p.ok = false;
+  return p;
+}
+
+template <int MODE>
+static int launch_bwd(const gn_csr& csr, const int32_t* ent_a, const int32_t* ent_b, const int32_t* ent_eid,
+                      const int64_t* src, const int64_t* dst, const float* coef, const float* z, int64_t ldz, int D,
+                      const float* w, float* outp, int64_t ldo, float* partial, cudaStream_t st) {
+  if (csr.n_rows == 0 || csr.n_chunks == 0) return GN_OK;
+  if (csr.n_chunks > csr.n_rows && !partial) return GN_ERR_ARG;
+  const bool v4 = (D % 4 == 0) && (ldz % 4 == 0) && (ldo % 4 == 0) && aligned16(z) && aligned16(outp) &&
+                  (!w || aligned16(w)) && (!partial || aligned16(partial));
+  const WidthPlan p = plan_width(D, v4);
+  if (!p.ok) return GN_ERR_ARG;
+  const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
+#define GN_BWD_CASE(L, V)                                                                                         \
+  if (p.lpe == L && p.vec == V) {                                                                                 \
+    GN_LAUNCH((distmult_bwd_kernel<L, V, MODE>), grid, 256, 0, st, csr, ent_a, ent_b, ent_eid, src, dst, coef, z, \
+              ldz, D, w, outp, ldo, partial);                                                                     \
+    return GN_OK;                                                                                                 \
+  }
+  GN_BWD_CASE(4, 4)
+  GN_BWD_CASE(8, 4)
+  GN_BWD_CASE(32, 4)
+  GN_BWD_CASE(4, 1)
+  GN_BWD_CASE(8, 1)
+  GN_BWD_CASE(32, 1)
+#undef GN_BWD_CASE
+  return GN_ERR_ARG;
+}
+
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" {
+
+int gn_distmult_fwd(const float* z, int64_t ldz, int32_t D, const float* w, const int64_t* src, const int64_t* dst,
+                    const int64_t* etype, int64_t n_edges, int sigmoid, float* out, void* stream) {
+  if (n_edges < 0 || D <= 0) return GN_ERR_ARG;
+  if (n_edges == 0) return GN_OK;
+  if (!z || !w || !src || !dst || !etype || !out) return GN_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  const bool v4 = (D % 4 == 0) && (ldz % 4 == 0) && aligned16(z) && aligned16(w);
+  const int units = v4 ? D / 4 : D;
+  const int lpe = units <= 32 ? 4 : (units <= 64 ? 8 : 32);
+  const int epi = 32 / lpe;
+  int64_t warps = ceil_div(n_edges, epi);
+  const int64_t max_warps = int64_t(148) * 64 * 4;
+  if (warps > max_warps) warps = max_warps;
+  const unsigned grid = (unsigned)ceil_div(warps, 8);
+#define GN_FWD_CASE(L, V)                                                                                           \
+  if (lpe == L && (v4 ? 4 : 1) == V) {                                                                              \
+    GN_LAUNCH((distmult_fwd_kernel<L, V>), grid, 256, 0, st, z, ldz, D, w, src, dst, etype, n_edges, sigmoid, out); \
+    return GN_OK;                                                                                                   \
+  }
+  GN_FWD_CASE(4, 4)
+  GN_FWD_CASE(8, 4)
+  GN_FWD_CASE(32, 4)
+  GN_FWD_CASE(4, 1)
+  GN_FWD_CASE(8, 1)
+  GN_FWD_CASE(32, 1)
+#undef GN_FWD_CASE
+  return GN_ERR_ARG;
+}
+
+int gn_distmult_coef(const float* grad_out, const float* out, int64_t n_edges, int sigmoid, float* coef,
+                     void* stream) {
+  if (n_edges < 0) return GN_ERR_ARG;
+  if (n_edges == 0) return GN_OK;
+  if (!grad_out || !coef || (sigmoid && !out)) return GN_ERR_ARG;
+  GN_LAUNCH(distmult_coef_kernel, (unsigned)ceil_div(n_edges, 256), 256, 0, as_stream(stream), grad_out, out, n_edges,
+            sigmoid, coef);
+  return GN_OK;
+}
+
+int gn_distmult_bwd_z(const gn_csr* node_csr, const int32_t* ent_other, const int32_t* ent_rel,
+                      const int32_t* ent_eid, const float* coef, const float* z, int64_t ldz, int32_t D,
+                      const float* w, float* dz, int64_t lddz, float* partial, void* stream) {
+  if (!node_csr || !z || !w || !dz || D <= 0) return GN_ERR_ARG;
+  if (node_csr->nnz > 0 && (!ent_other || !ent_rel || !ent_eid || !coef)) return GN_ERR_ARG;
+  return launch_bwd<0>(*node_csr, ent_other, ent_rel, ent_eid, nullptr, nullptr, coef, z, ldz, D, w, dz, lddz,
+                       partial, as_stream(stream));
+}
+
+int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64_t* src, const int64_t* dst,
+                      const float* coef, const float* z, int64_t ldz, int32_t D, float* dw, float* partial,
+                      void* stream) {
+  if (!rel_csr || !z || !dw || D <= 0) return GN_ERR_ARG;
+  if (rel_csr->nnz > 0 && (!rel_eid || !src || !dst || !coef)) return GN_ERR_ARG;
+  return launch_bwd<1>(*rel_csr, nullptr, nullptr, rel_eid, src, dst, coef, z, ldz, D, nullptr, dw, D, partial,
+                       as_stream(stream));
+}
+
+int gn_softmax_fwd(const float* logits, int64_t n, int32_t C, float* out, void* stream) {
+  if (n < 0 || C <= 0) return GN_ERR_ARG;
+  if (n == 0) return GN_OK;
+  if (!logits || !out) return GN_ERR_ARG;
+  GN_LAUNCH(softmax_fwd_kernel, (unsigned)ceil_div(n * 32, 256), 256, 0, as_stream(stream), logits, n, C, out);
+  return GN_OK;
+}
+
+int gn_softmax_bwd(const float* out, const float* grad_out, int64_t n, int32_t C, float* grad_logits, void* stream) {
+  if (n < 0 || C <= 0) return GN_ERR_ARG;
+  if (n == 0) return GN_OK;
+  if (!out || !grad_out || !grad_logits) return GN_ERR_ARG;
+  GN_LAUNCH(softmax_bwd_kernel, (unsigned)ceil_div(n * 32, 256), 256, 0, as_stream(stream), out, grad_out, n, C,
+            grad_logits);
+  return GN_OK;
+}
+
+}  // extern "C"

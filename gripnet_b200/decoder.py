@@ -1,0 +1,49 @@
+"""Drop-in ``gripnet.decoder`` on the CUDA path (reference ``gripnet/decoder.py``)."""
+import math
+
+import torch
+from torch.nn import Module, Parameter
+
+from . import ops
+
+
+class multiRelaInnerProductDecoder(Module):
+    """DistMult link decoder ``sigmoid(sum_k z[s,k] z[d,k] w[r,k])`` (``decoder.py:10-26``).
+
+    One fused gather-multiply-reduce kernel; nothing of size ``[E, in_dim]`` is
+    materialised, so the reference's activation checkpointing
+    (``GripNet-pose.py:133-135``) is unnecessary.  The backward is atomic-free.
+    """
+
+    def __init__(self, in_dim, num_et):
+        super().__init__()
+        self.num_et, self.in_dim = num_et, in_dim
+        self.weight = Parameter(torch.empty(num_et, in_dim))
+        self.reset_parameters()
+
+    def forward(self, z, edge_index, edge_type, sigmoid=True):
+        return ops.DistMult.apply(z, self.weight, edge_index, edge_type, bool(sigmoid))
+
+    def reset_parameters(self):
+        with torch.no_grad():
+            self.weight.normal_(std=1.0 / math.sqrt(self.in_dim))          # decoder.py:25-26
+
+
+class multiClassInnerProductDecoder(Module):
+    """``softmax(z[node_list] W)`` (``decoder.py:29-50``): row-gather GEMM + softmax kernels."""
+
+    def __init__(self, in_dim, num_class):
+        super().__init__()
+        self.num_class, self.in_dim = num_class, in_dim
+        self.weight = Parameter(torch.empty(in_dim, num_class))
+        self.reset_parameters()
+
+    def forward(self, z, node_list, softmax=True):
+        if not torch.is_tensor(node_list):
+            node_list = torch.as_tensor(node_list, dtype=torch.int64, device=z.device)
+        return ops.MultiClass.apply(z, self.weight, node_list, bool(softmax))
+
+    def reset_parameters(self):
+        bound = math.sqrt(6.0 / (self.in_dim + self.num_class))            # decoder.py:47-49
+        with torch.no_grad():
+            self.weight.uniform_(-bound, bound)

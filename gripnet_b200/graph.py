@@ -1,0 +1,304 @@
+"""Device-resident graph structures built by the K1 preprocessing kernels.
+
+``edge_index`` (int64 ``[2,E]``) is turned once into a destination-sorted CSR and
+its transpose (stable counting sort => bit-exact edge order), with the GCN
+symmetric normalisation precomputed, and cached per tensor identity — the
+counterpart of ``myGCN.cached_result`` (reference ``gripnet/layers.py:83-90``).
+All arrays live in HBM as int32 / fp32 tensors owned by these objects.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+
+_SM_COUNT = 148
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t, name, dtype=None):
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"gripnet_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"gripnet_b200: {name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def pick_chunk_len(nnz):
+    """Entries per warp-chunk: enough chunks to fill 148 SMs x 32 warps, within [32, 1024]."""
+    target = max(1, nnz // (_SM_COUNT * 32))
+    c = 32
+    while c * 2 <= target and c < 1024:
+        c *= 2
+    return c
+
+
+class Csr:
+    """Device CSR + row-split chunk list (mirror of ``gn_csr``)."""
+
+    def __init__(self, rowptr, col, val, n_rows, n_cols, nnz_bound, exact=True, chunk_len=None):
+        lib = _lib.load()
+        dev = rowptr.device
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.nnz = int(nnz_bound)
+        self.chunk_len = int(chunk_len or pick_chunk_len(self.nnz))
+        cap = self.n_rows + self.nnz // self.chunk_len + 1
+        self.chunk_ptr = torch.empty(self.n_rows + 1, dtype=torch.int32, device=dev)
+        self.chunk_row = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.chunk_beg = torch.empty(cap, dtype=torch.int32, device=dev)
+        self.row_counter = torch.zeros(max(self.n_rows, 1), dtype=torch.int32, device=dev)
+        ws = _ws(lib.gn_build_chunks_workspace_bytes(self.n_rows), dev)
+        _lib.check(lib.gn_build_chunks(_ptr(rowptr), self.n_rows, self.chunk_len, _ptr(self.chunk_ptr),
+                                       _ptr(self.chunk_row), _ptr(self.chunk_beg), cap, _ptr(ws), ws.numel(),
+                                       _stream()), "gn_build_chunks")
+        if exact:   # one host read at graph-build time (never inside a captured step)
+            self.n_chunks = int(self.chunk_ptr[self.n_rows].item()) if self.n_rows > 0 else 0
+        else:
+            self.n_chunks = cap - 1 if self.n_rows > 0 else 0
+        self.c = _lib.GnCsr(self.n_rows, self.n_cols, self.nnz, self.chunk_len, self.n_chunks, 0,
+                            _ptr(rowptr), _ptr(col), _ptr(val), _ptr(self.chunk_ptr), _ptr(self.chunk_row),
+                            _ptr(self.chunk_beg), _ptr(self.row_counter))
+        self.ref = C.byref(self.c)
+
+    @property
+    def extra_chunks(self):
+        return max(0, self.n_chunks - self.n_rows)
+
+    def partial(self, width):
+        """Scratch for rows split over several chunks (2 slots per extra chunk), or None."""
+        if self.extra_chunks == 0:
+            return None
+        return torch.empty(2 * self.extra_chunks * int(width), dtype=torch.float32, device=self.rowptr.device)
+
+
+class GcnGraph:
+    """dst-sorted CSR (forward) + src-sorted CSR (backward) with GCN normalisation."""
+
+    def __init__(self, edge_index, n_src, n_dst, edge_weight=None, improved=False, bipartite=False,
+                 want_aug=False):
+        lib = _lib.load()
+        require_cuda(edge_index, "edge_index", torch.int64)
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise RuntimeError("edge_index must have shape [2, E]")
+        dev = edge_index.device
+        E = int(edge_index.size(1))
+        if E + n_dst >= 2 ** 31 or n_src >= 2 ** 31:
+            raise RuntimeError("gripnet_b200: graph exceeds the int32 index space (N, E + N must be < 2^31)")
+        ei = edge_index.contiguous()
+        w = None
+        if edge_weight is not None:
+            w = require_cuda(edge_weight, "edge_weight").to(torch.float32).contiguous()
+            if w.numel() != E:
+                raise RuntimeError("edge_weight must have one entry per edge")
+        if E > 0:
+            lo, hi0, hi1 = int(ei.min()), int(ei[0].max()), int(ei[1].max())
+            if lo < 0 or hi0 >= n_src or hi1 >= n_dst:
+                raise IndexError("edge_index out of range for the given node counts")
+        self.n_src, self.n_dst, self.n_edges, self.bipartite = int(n_src), int(n_dst), E, bool(bipartite)
+        cap = E + (0 if bipartite else n_dst)
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        rowptr = torch.empty(n_dst + 1, **i32)
+        col = torch.empty(max(cap, 1), **i32)
+        val = torch.empty(max(cap, 1), **f32)
+        perm = torch.empty(max(cap, 1), **i32)
+        rowptr_t = torch.empty(n_src + 1, **i32)
+        col_t = torch.empty(max(cap, 1), **i32)
+        val_t = torch.empty(max(cap, 1), **f32)
+        perm_t = torch.empty(max(cap, 1), **i32)
+        self.deg = torch.empty(n_dst, **f32)
+        self.indeg = torch.empty(n_dst, **i32)
+        counts = torch.zeros(4, **i32)
+        aug_idx = aug_norm = None
+        if want_aug and not bipartite:
+            aug_idx = torch.empty(2, max(cap, 1), dtype=torch.int64, device=dev)
+            aug_norm = torch.empty(max(cap, 1), **f32)
+        ws = _ws(lib.gn_gcn_prep_workspace_bytes(E, n_src, n_dst), dev)
+        fill = 2.0 if improved else 1.0
+        _lib.check(lib.gn_gcn_prep(
+            _ptr(ei[0]) if E else None, _ptr(ei[1]) if E else None, _ptr(w), E, n_src, n_dst, int(bipartite), fill,
+            _ptr(aug_idx[0]) if aug_idx is not None else None, _ptr(aug_idx[1]) if aug_idx is not None else None,
+            _ptr(aug_norm), _ptr(rowptr), _ptr(col), _ptr(val), _ptr(perm), _ptr(rowptr_t), _ptr(col_t),
+            _ptr(val_t), _ptr(perm_t), _ptr(self.deg), _ptr(self.indeg), _ptr(counts), _ptr(ws), ws.numel(),
+            _stream()), "gn_gcn_prep")
+        self.nnz = int(counts[0].item())           # E' (one host read, at graph-build time)
+        self.perm, self.perm_t = perm[: self.nnz], perm_t[: self.nnz]
+        self.fwd = Csr(rowptr, col, val, n_dst, n_src, self.nnz)
+        self.bwd = Csr(rowptr_t, col_t, val_t, n_src, n_dst, self.nnz)
+        if aug_idx is not None:
+            self.aug_edge_index = aug_idx[:, : self.nnz]
+            self.aug_norm = aug_norm[: self.nnz]
+        else:
+            self.aug_edge_index = self.aug_norm = None
+
+
+class RgcnGraph:
+    """Relation-aware CSR pair for myRGCN (joint mean over all in-edges)."""
+
+    def __init__(self, edge_index, range_list, n_nodes, n_rel):
+        lib = _lib.load()
+        require_cuda(edge_index, "edge_index", torch.int64)
+        dev = edge_index.device
+        E = int(edge_index.size(1))
+        rl = torch.as_tensor(range_list).to(torch.int64)
+        rl_host = rl.cpu()
+        if rl_host.dim() != 2 or rl_host.size(1) != 2 or rl_host.size(0) != n_rel:
+            raise RuntimeError("range_list must have shape [num_relations, 2]")
+        # the reference concatenates the per-relation slices and scatters them at
+        # edge_index[1] positionally (layers.py:178-189): only an ascending partition
+        # of [0, E) is meaningful there, anything else mis-sizes its scatter.
+        flat = rl_host.flatten().tolist()
+        ok = flat[0] == 0 and flat[-1] == E and all(flat[2 * r + 1] == flat[2 * r + 2] for r in range(n_rel - 1)) \
+            and all(flat[2 * r] <= flat[2 * r + 1] for r in range(n_rel))
+        if not ok:
+            raise RuntimeError("range_list must partition [0, E) into ascending contiguous [start, end) slices")
+        if n_nodes * n_rel >= 2 ** 31 or E >= 2 ** 31:
+            raise RuntimeError("gripnet_b200: num_nodes * num_relations must be < 2^31")
+        ei = edge_index.contiguous()
+        if E > 0 and (int(ei.min()) < 0 or int(ei.max()) >= n_nodes):
+            raise IndexError("edge_index out of range")
+        rl_dev = rl.to(dev).contiguous()
+        self.n_nodes, self.n_rel, self.n_edges = int(n_nodes), int(n_rel), E
+        i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        rowptr = torch.empty(n_nodes + 1, **i32)
+        col = torch.empty(max(E, 1), **i32)
+        self.perm = torch.empty(max(E, 1), **i32)
+        self.inv_cnt = torch.empty(n_nodes, **f32)
+        rowptr_t = torch.empty(n_nodes * n_rel + 1, **i32)
+        col_t = torch.empty(max(E, 1), **i32)
+        val_t = torch.empty(max(E, 1), **f32)
+        self.perm_t = torch.empty(max(E, 1), **i32)
+        ws = _ws(lib.gn_rgcn_prep_workspace_bytes(E, n_nodes, n_rel), dev)
+        _lib.check(lib.gn_rgcn_prep(_ptr(ei[0]) if E else None, _ptr(ei[1]) if E else None, E, _ptr(rl_dev), n_nodes,
+                                    n_rel, _ptr(rowptr), _ptr(col), _ptr(self.perm), _ptr(self.inv_cnt),
+                                    _ptr(rowptr_t), _ptr(col_t), _ptr(val_t), _ptr(self.perm_t), _ptr(ws),
+                                    ws.numel(), _stream()), "gn_rgcn_prep")
+        self.fwd = Csr(rowptr, col, None, n_nodes, n_nodes * n_rel, E)
+        self.bwd = Csr(rowptr_t, col_t, val_t, n_nodes * n_rel, n_nodes, E)
+
+
+class EdgeStruct:
+    """Endpoint CSR + relation CSR of an edge list (deterministic DistMult backward)."""
+
+    def __init__(self, edge_index, edge_type, n_nodes, n_rel, exact):
+        lib = _lib.load()
+        dev = edge_index.device
+        E = int(edge_index.size(1))
+        if 2 * E >= 2 ** 31:
+            raise RuntimeError("gripnet_b200: 2*E must be < 2^31")
+        ei = edge_index.contiguous()
+        et = edge_type.contiguous()
+        self.edge_index, self.edge_type = ei, et
+        i32 = dict(dtype=torch.int32, device=dev)
+        node_rowptr = torch.empty(n_nodes + 1, **i32)
+        self.ent_other = torch.empty(max(2 * E, 1), **i32)
+        self.ent_rel = torch.empty(max(2 * E, 1), **i32)
+        self.ent_eid = torch.empty(max(2 * E, 1), **i32)
+        rel_rowptr = torch.empty(n_rel + 1, **i32)
+        self.rel_eid = torch.empty(max(E, 1), **i32)
+        ws = _ws(lib.gn_edge_prep_workspace_bytes(E, n_nodes, n_rel), dev)
+        _lib.check(lib.gn_edge_prep(_ptr(ei[0]) if E else None, _ptr(ei[1]) if E else None, _ptr(et) if E else None,
+                                    E, n_nodes, n_rel, _ptr(node_rowptr), _ptr(self.ent_other), _ptr(self.ent_rel),
+                                    _ptr(self.ent_eid), _ptr(rel_rowptr), _ptr(self.rel_eid), _ptr(ws), ws.numel(),
+                                    _stream()), "gn_edge_prep")
+        self.node = Csr(node_rowptr, self.ent_other, None, n_nodes, n_nodes, 2 * E, exact=exact)
+        self.rel = Csr(rel_rowptr, self.rel_eid, None, n_rel, max(E, 1), E, exact=exact)
+
+
+class IndexStruct:
+    """CSR of an index list: row n lists the positions i with index[i] == n."""
+
+    def __init__(self, index, n_nodes, exact=True):
+        lib = _lib.load()
+        dev = index.device
+        n = int(index.numel())
+        idx = index.contiguous()
+        if n > 0 and exact and (int(idx.min()) < 0 or int(idx.max()) >= n_nodes):
+            raise IndexError("node_list out of range")
+        rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+        self.perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        ws = _ws(lib.gn_index_prep_workspace_bytes(n, n_nodes), dev)
+        _lib.check(lib.gn_index_prep(_ptr(idx) if n else None, n, n_nodes, _ptr(rowptr), _ptr(self.perm), _ptr(ws),
+                                     ws.numel(), _stream()), "gn_index_prep")
+        self.csr = Csr(rowptr, self.perm, None, n_nodes, max(n, 1), n, exact=exact)
+
+
+# --------------------------------------------------------------------------
+# structure cache, keyed by tensor identity (the cache entry keeps the key
+# tensors alive, so their storage cannot be recycled under a stale entry)
+# --------------------------------------------------------------------------
+class _Cache:
+    def __init__(self, capacity=16):
+        self.capacity = capacity
+        self.store = OrderedDict()
+
+    @staticmethod
+    def tkey(t):
+        if t is None:
+            return None
+        return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t._version, str(t.dtype))
+
+    def get(self, key, tensors, build):
+        hit = self.store.get(key)
+        if hit is not None:
+            self.store.move_to_end(key)
+            return hit[0]
+        obj = build()
+        self.store[key] = (obj, tensors)
+        while len(self.store) > self.capacity:
+            self.store.popitem(last=False)
+        return obj
+
+    def clear(self):
+        self.store.clear()
+
+
+_cache = _Cache()
+
+
+def clear_cache():
+    _cache.clear()
+
+
+def _capturing():
+    return torch.cuda.is_current_stream_capturing()
+
+
+def gcn_graph(edge_index, n_src, n_dst, edge_weight=None, improved=False, bipartite=False, want_aug=False):
+    key = ("gcn", _Cache.tkey(edge_index), _Cache.tkey(edge_weight), n_src, n_dst, improved, bipartite, want_aug)
+    return _cache.get(key, (edge_index, edge_weight),
+                      lambda: GcnGraph(edge_index, n_src, n_dst, edge_weight, improved, bipartite, want_aug))
+
+
+def rgcn_graph(edge_index, range_list, n_nodes, n_rel):
+    key = ("rgcn", _Cache.tkey(edge_index), _Cache.tkey(range_list), n_nodes, n_rel)
+    return _cache.get(key, (edge_index, range_list), lambda: RgcnGraph(edge_index, range_list, n_nodes, n_rel))
+
+
+def edge_struct(edge_index, edge_type, n_nodes, n_rel):
+    key = ("edge", _Cache.tkey(edge_index), _Cache.tkey(edge_type), n_nodes, n_rel)
+    exact = not _capturing()
+    return _cache.get(key, (edge_index, edge_type),
+                      lambda: EdgeStruct(edge_index, edge_type, n_nodes, n_rel, exact))
+
+
+def index_struct(index, n_nodes):
+    key = ("index", _Cache.tkey(index), n_nodes)
+    exact = not _capturing()
+    return _cache.get(key, (index,), lambda: IndexStruct(index, n_nodes, exact))

@@ -1,0 +1,616 @@
+"""``torch.autograd.Function`` wrappers over the C ABI (``include/gripnet_b200.h``).
+
+Each Function covers a whole module-level stage (a stack of GCN / RGCN layers, a
+decoder, a loss) so that intermediate tensors the reference materialises — the
+``[E,F]`` message tensors, ``[E,D]`` decoder gathers, zero-padded inter-graph
+inputs, ``torch.cat`` copies — never exist, and so that ReLU masks / concat-slice
+gradients are fused into the producing kernels' epilogues.
+
+PyTorch is used for device memory (``torch.empty``) and streams only; every
+arithmetic step is a kernel of ``libgripnet_b200.so``.
+"""
+import torch
+
+from . import _lib
+from .graph import _ptr, _stream, _ws, require_cuda
+
+EPS = 1e-13  # reference gripnet/utils.py:10
+
+
+class M:
+    """A row-major fp32 matrix view: (tensor kept alive, pointer, leading dim, rows, cols)."""
+    __slots__ = ("t", "ptr", "ld", "n", "f")
+
+    def __init__(self, t, col0=0, width=None):
+        assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == torch.float32
+        self.t = t
+        self.n = t.size(0)
+        self.f = t.size(1) - col0 if width is None else width
+        self.ld = t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
+        self.ptr = t.data_ptr() + 4 * col0
+
+
+def _as_rows(x, name):
+    """fp32 CUDA matrix with unit column stride (copy only if needed)."""
+    require_cuda(x, name)
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"gripnet_b200: {name} must be float32")
+    if x.dim() != 2:
+        raise RuntimeError(f"gripnet_b200: {name} must be 2-D")
+    if x.stride(1) != 1 or (x.size(0) > 1 and x.stride(0) < x.size(1)):
+        x = x.contiguous()
+    return x
+
+
+def _new(n, f, like):
+    return torch.empty((n, f), dtype=torch.float32, device=like.device)
+
+
+# ----------------------------------------------------------------------------
+# thin kernel wrappers
+# ----------------------------------------------------------------------------
+def spmm(csr, x, out, F, row_scale=None, bias=None, addend=None, relu=False):
+    lib = _lib.load()
+    partial = csr.partial(min(F, 128))
+    _lib.check(lib.gn_spmm(csr.ref, x.ptr, x.ld, F, _ptr(row_scale), _ptr(bias),
+                           addend.ptr if addend is not None else None, addend.ld if addend is not None else 0,
+                           int(relu), out.ptr, out.ld, _ptr(partial), _stream()), "gn_spmm")
+
+
+_SPLITK_TARGET = 148 * 2
+
+
+def sgemm(ta, tb, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, device, batch=1, sa=0, sb=0, sc=0, batch_reduce=False,
+          alpha=1.0, accumulate=False, addend=None, mask=None, a_rows=None, split_k=False):
+    lib = _lib.load()
+    splits, ws, ws_bytes = 1, None, 0
+    if split_k and batch == 1 and k >= 1024:
+        tiles = ((m + 63) // 64) * ((n + 63) // 64)
+        splits = max(1, min(_SPLITK_TARGET // max(tiles, 1), k // 256))
+        if splits > 1:
+            ws = torch.empty(splits * m * n, dtype=torch.float32, device=device)
+            ws_bytes = ws.numel() * 4
+    _lib.check(lib.gn_sgemm(int(ta), int(tb), m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc,
+                            int(batch_reduce), float(alpha), int(accumulate),
+                            addend.ptr if addend is not None else None, addend.ld if addend is not None else 0,
+                            mask.ptr if mask is not None else None, mask.ld if mask is not None else 0,
+                            _ptr(a_rows), splits, _ptr(ws), ws_bytes, _stream()), "gn_sgemm")
+
+
+def map2d(op, src, dst):
+    _lib.check(_lib.load().gn_map2d(op, src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.f, _stream()), "gn_map2d")
+
+
+def relu_bwd(g, y, dst):
+    _lib.check(_lib.load().gn_relu_bwd(g.ptr, g.ld, y.ptr, y.ld, dst.ptr, dst.ld, g.n, g.f, _stream()), "gn_relu_bwd")
+
+
+def colsum(x, out):
+    lib = _lib.load()
+    ws = _ws(lib.gn_colsum_workspace_bytes(x.n, x.f), out.device)
+    _lib.check(lib.gn_colsum(x.ptr, x.ld, x.n, x.f, _ptr(out), _ptr(ws), ws.numel(), _stream()), "gn_colsum")
+
+
+# ----------------------------------------------------------------------------
+# GCN stack:  H_l = act_l( A_hat (H_{l-1} W_l) + b_l ),  optional concat of all H_l
+#   reference: myGCN.forward (layers.py:71-100) inside homoGraph.forward (:252-318)
+#   and interGraph.forward (:362-370, rectangular A_hat)
+# ----------------------------------------------------------------------------
+class GcnStack(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, graph, relu_flags, catout, *params):
+        n_layers = len(relu_flags)
+        weights = [params[2 * l] for l in range(n_layers)]
+        biases = [params[2 * l + 1] for l in range(n_layers)]
+        x0 = _as_rows(x0, "x")
+        if x0.size(0) != graph.n_src:
+            raise RuntimeError(f"x has {x0.size(0)} rows but the graph has {graph.n_src} source nodes")
+        if catout and graph.n_src != graph.n_dst:
+            raise RuntimeError("if_catout needs a square graph")
+        dims = [x0.size(1)] + [w.size(1) for w in weights]
+        for l, w in enumerate(weights):
+            require_cuda(w, "weight", torch.float32)
+            if w.size(0) != dims[l]:
+                raise RuntimeError(f"layer {l}: weight expects {w.size(0)} input features, got {dims[l]}")
+        dev = x0.device
+        outs = []      # M views of H_0 .. H_L
+        if catout:
+            buf = _new(graph.n_dst, sum(dims), x0)
+            offs = [sum(dims[:i]) for i in range(len(dims))]
+            h0 = M(buf, offs[0], dims[0])
+            map2d(_lib.EW_COPY, M(x0), h0)
+            outs.append(h0)
+        else:
+            buf = None
+            outs.append(M(x0))
+        for l in range(n_layers):
+            w = weights[l].contiguous()
+            k, f = dims[l], dims[l + 1]
+            y = _new(graph.n_src, f, x0)
+            xin = outs[l]
+            sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.data_ptr(), f, dev)
+            if catout:
+                hl = M(buf, offs[l + 1], f)
+            else:
+                hl = M(_new(graph.n_dst, f, x0))
+            b = biases[l].contiguous() if biases[l] is not None else None
+            spmm(graph.fwd, M(y), hl, f, bias=b, relu=relu_flags[l])
+            outs.append(hl)
+        ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
+        ctx.has_bias = [b is not None for b in biases]
+        ws = [w.contiguous() for w in weights]
+        # outputs/intermediates go through save_for_backward (no ctx <-> output reference cycle)
+        acts = [buf] if catout else [o.t for o in outs]
+        ctx.n_acts = len(acts)
+        ctx.save_for_backward(*acts, *ws)
+        return buf if catout else outs[-1].t
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        graph, relu_flags, catout, dims = ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims
+        n_layers = len(relu_flags)
+        saved = ctx.saved_tensors
+        acts, weights = saved[: ctx.n_acts], saved[ctx.n_acts:]
+        if catout:
+            offs0 = [sum(dims[:i]) for i in range(len(dims))]
+            outs = [M(acts[0], offs0[i], dims[i]) for i in range(len(dims))]
+        else:
+            outs = [M(a) for a in acts]
+        g = _as_rows(grad_out, "grad")
+        dev = g.device
+        if catout:
+            offs = [sum(dims[:i]) for i in range(len(dims))]
+            gs = [M(g, offs[i], dims[i]) for i in range(len(dims))]
+            dh = gs[n_layers]
+        else:
+            gs = None
+            dh = M(g)
+        grads = [None] * (2 * n_layers)
+        dz_ready = False          # True when `dh` already carries the ReLU mask of its own layer
+        dx0 = None
+        for l in range(n_layers, 0, -1):
+            f, k = dims[l], dims[l - 1]
+            h_l, h_prev = outs[l], outs[l - 1]
+            if relu_flags[l - 1] and not dz_ready:
+                dz = M(_new(graph.n_dst, f, g))
+                relu_bwd(dh, h_l, dz)
+            else:
+                dz = dh
+            if ctx.has_bias[l - 1] and ctx.needs_input_grad[4 + 2 * (l - 1) + 1]:
+                db = torch.empty(f, dtype=torch.float32, device=dev)
+                colsum(dz, db)
+                grads[2 * (l - 1) + 1] = db
+            dy = M(_new(graph.n_src, f, g))
+            spmm(graph.bwd, dz, dy, f)
+            if ctx.needs_input_grad[4 + 2 * (l - 1)]:
+                dw = torch.empty((k, f), dtype=torch.float32, device=dev)
+                # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
+                sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f, dev,
+                      split_k=True)
+                grads[2 * (l - 1)] = dw
+            need_prev = (l > 1) or ctx.needs_input_grad[0]
+            if need_prev:
+                w = weights[l - 1]
+                dprev = M(_new(graph.n_src, k, g))
+                addend = gs[l - 1] if catout else None
+                mask = h_prev if (l > 1 and relu_flags[l - 2]) else None
+                # dH_{l-1} = dY W^T (+ concat-slice grad) (masked by ReLU of layer l-1)
+                sgemm(False, True, graph.n_src, k, f, dy.ptr, dy.ld, w.data_ptr(), f, dprev.ptr, dprev.ld, dev,
+                      addend=addend, mask=mask)
+                dh = dprev
+                dz_ready = mask is not None
+                if l == 1:
+                    dx0 = dprev.t
+        return (dx0, None, None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------------
+# RGCN stack: H_l = relu( mean_{e->i} H_{l-1}[src_e] W_{r(e)} + H_{l-1} root (+ b) )
+#   reference: myRGCN (layers.py:165-197) inside homoGraph.forward (:268-309)
+# ----------------------------------------------------------------------------
+class RgcnStack(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, graph, relu_flags, catout, *params):
+        n_layers = len(relu_flags)
+        basis = [params[4 * l] for l in range(n_layers)]
+        att = [params[4 * l + 1] for l in range(n_layers)]
+        root = [params[4 * l + 2] for l in range(n_layers)]
+        bias = [params[4 * l + 3] for l in range(n_layers)]
+        x0 = _as_rows(x0, "x")
+        n, r = graph.n_nodes, graph.n_rel
+        if x0.size(0) != n:
+            raise RuntimeError(f"x has {x0.size(0)} rows but the graph has {n} nodes")
+        dims = [x0.size(1)] + [rt.size(1) for rt in root]
+        dev = x0.device
+        outs, ws_list = [], []
+        if catout:
+            buf = _new(n, sum(dims), x0)
+            offs = [sum(dims[:i]) for i in range(len(dims))]
+            h0 = M(buf, offs[0], dims[0])
+            map2d(_lib.EW_COPY, M(x0), h0)
+            outs.append(h0)
+        else:
+            buf = None
+            outs.append(M(x0))
+        for l in range(n_layers):
+            k, f = dims[l], dims[l + 1]
+            nb = basis[l].size(0)
+            if att[l].size(0) != r:
+                raise RuntimeError("att rows must equal the number of relations of the graph")
+            bs, at, rt = basis[l].contiguous(), att[l].contiguous(), root[l].contiguous()
+            # W[r] = sum_b att[r,b] basis[b]   (layers.py:172-173)
+            w = torch.empty((r, k, f), dtype=torch.float32, device=dev)
+            sgemm(False, False, r, k * f, nb, at.data_ptr(), nb, bs.data_ptr(), k * f, w.data_ptr(), k * f, dev)
+            xin = outs[l]
+            # Y[:, r, :] = X W[r] for every relation at once (transform-then-gather)
+            y = torch.empty((n, r, f), dtype=torch.float32, device=dev)
+            sgemm(False, False, n, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.data_ptr(), r * f, dev,
+                  batch=r, sa=0, sb=k * f, sc=f)
+            hl = M(buf, offs[l + 1], f) if catout else M(_new(n, f, x0))
+            # root term first, then the segmented mean accumulates onto it (layers.py:193)
+            sgemm(False, False, n, f, k, xin.ptr, xin.ld, rt.data_ptr(), f, hl.ptr, hl.ld, dev)
+            b = bias[l].contiguous() if bias[l] is not None else None
+            spmm(graph.fwd, M(y.view(n * r, f)), hl, f, row_scale=graph.inv_cnt, bias=b, addend=hl,
+                 relu=relu_flags[l])
+            outs.append(hl)
+            ws_list.append((w, bs, at, rt))
+        ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
+        ctx.has_bias = [b is not None for b in bias]
+        acts = [buf] if catout else [o.t for o in outs]
+        ctx.n_acts = len(acts)
+        flat = [t for tup in ws_list for t in tup]
+        ctx.save_for_backward(*acts, *flat)
+        return buf if catout else outs[-1].t
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        graph, relu_flags, catout, dims = ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims
+        n_layers = len(relu_flags)
+        n, r = graph.n_nodes, graph.n_rel
+        saved = ctx.saved_tensors
+        acts, flat = saved[: ctx.n_acts], saved[ctx.n_acts:]
+        ws_list = [tuple(flat[4 * i: 4 * i + 4]) for i in range(n_layers)]
+        if catout:
+            offs0 = [sum(dims[:i]) for i in range(len(dims))]
+            outs = [M(acts[0], offs0[i], dims[i]) for i in range(len(dims))]
+        else:
+            outs = [M(a) for a in acts]
+        g = _as_rows(grad_out, "grad")
+        dev = g.device
+        if catout:
+            offs = [sum(dims[:i]) for i in range(len(dims))]
+            gs = [M(g, offs[i], dims[i]) for i in range(len(dims))]
+            dh = gs[n_layers]
+        else:
+            gs = None
+            dh = M(g)
+        grads = [None] * (4 * n_layers)
+        dz_ready = False
+        dx0 = None
+        for l in range(n_layers, 0, -1):
+            f, k = dims[l], dims[l - 1]
+            w, bs, at, rt = ws_list[l - 1]
+            nb = bs.size(0)
+            h_l, h_prev = outs[l], outs[l - 1]
+            if relu_flags[l - 1] and not dz_ready:
+                dz = M(_new(n, f, g))
+                relu_bwd(dh, h_l, dz)
+            else:
+                dz = dh
+            base = 4 + 4 * (l - 1)
+            if ctx.has_bias[l - 1] and ctx.needs_input_grad[base + 3]:
+                db = torch.empty(f, dtype=torch.float32, device=dev)
+                colsum(dz, db)
+                grads[4 * (l - 1) + 3] = db
+            # dY[(j,r)] = sum_{e: src=j, rel=r} dZ[dst_e] / c_dst   (transpose CSR, atomic-free)
+            dy = torch.empty((n * r, f), dtype=torch.float32, device=dev)
+            spmm(graph.bwd, dz, M(dy), f)
+            if ctx.needs_input_grad[base + 2]:
+                droot = torch.empty((k, f), dtype=torch.float32, device=dev)
+                sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev,
+                      split_k=True)
+                grads[4 * (l - 1) + 2] = droot
+            if ctx.needs_input_grad[base] or ctx.needs_input_grad[base + 1]:
+                # dW[r] = H_{l-1}^T dY[:, r, :]
+                dw = torch.empty((r, k, f), dtype=torch.float32, device=dev)
+                sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dy.data_ptr(), r * f, dw.data_ptr(), f, dev,
+                      batch=r, sa=0, sb=f, sc=k * f)
+                if ctx.needs_input_grad[base + 1]:
+                    datt = torch.empty((r, nb), dtype=torch.float32, device=dev)
+                    sgemm(False, True, r, nb, k * f, dw.data_ptr(), k * f, bs.data_ptr(), k * f, datt.data_ptr(), nb,
+                          dev)
+                    grads[4 * (l - 1) + 1] = datt
+                if ctx.needs_input_grad[base]:
+                    dbasis = torch.empty((nb, k, f), dtype=torch.float32, device=dev)
+                    sgemm(True, False, nb, k * f, r, at.data_ptr(), nb, dw.data_ptr(), k * f, dbasis.data_ptr(),
+                          k * f, dev)
+                    grads[4 * (l - 1)] = dbasis
+            need_prev = (l > 1) or ctx.needs_input_grad[0]
+            if need_prev:
+                dprev = M(_new(n, k, g))
+                addend = gs[l - 1] if catout else None
+                mask = h_prev if (l > 1 and relu_flags[l - 2]) else None
+                # dH_{l-1} = dZ root^T (+ concat grad), then += sum_r dY[:, r, :] W[r]^T, then ReLU mask
+                sgemm(False, True, n, k, f, dz.ptr, dz.ld, rt.data_ptr(), f, dprev.ptr, dprev.ld, dev, addend=addend)
+                sgemm(False, True, n, k, f, dy.data_ptr(), r * f, w.data_ptr(), f, dprev.ptr, dprev.ld, dev,
+                      batch=r, sa=f, sb=k * f, sc=0, batch_reduce=True, accumulate=True, mask=mask)
+                dh = dprev
+                dz_ready = mask is not None
+                if l == 1:
+                    dx0 = dprev.t
+        return (dx0, None, None, None) + tuple(grads)
+
+
+# ----------------------------------------------------------------------------
+# interGraph tail: cat([h, |t|]) / (h+|t|)/2 / (h+relu(t D))/2   (layers.py:375-384)
+# ----------------------------------------------------------------------------
+def axpby(a, alpha, b, beta, dst):
+    _lib.check(_lib.load().gn_axpby(a.ptr, a.ld, float(alpha), b.ptr if b is not None else None,
+                                    b.ld if b is not None else 0, float(beta), dst.ptr, dst.ld, a.n, a.f,
+                                    _stream()), "gn_axpby")
+
+
+def abs_bwd(g, t, dst, scale):
+    _lib.check(_lib.load().gn_abs_bwd(g.ptr, g.ld, t.ptr, t.ld, dst.ptr, dst.ld, g.n, g.f, float(scale),
+                                      _stream()), "gn_abs_bwd")
+
+
+class InterTail(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, target_feat, target_feat_down, mod):
+        h = _as_rows(h, "h")
+        t = _as_rows(target_feat, "target_feat")
+        n, f, ft = h.size(0), h.size(1), t.size(1)
+        if t.size(0) != n:
+            raise RuntimeError("target_feat rows must equal the number of target nodes")
+        dev = h.device
+        ctx.shapes = (n, f, ft)
+        if mod == "cat":
+            out = _new(n, f + ft, h)
+            map2d(_lib.EW_COPY, M(h), M(out, 0, f))
+            map2d(_lib.EW_ABS, M(t), M(out, f, ft))
+            ctx.kind = 0
+            ctx.save_for_backward(t)
+            return out
+        out = _new(n, f, h)
+        if f == ft:
+            map2d(_lib.EW_ABS, M(t), M(out))
+            ctx.kind = 1
+            ctx.save_for_backward(t)
+        else:
+            d = _as_rows(target_feat_down, "target_feat_down")
+            u = _new(n, f, h)
+            sgemm(False, False, n, f, ft, t.data_ptr(), t.stride(0), d.data_ptr(), d.stride(0), u.data_ptr(), f, dev)
+            map2d(_lib.EW_RELU, M(u), M(out))
+            ctx.kind = 2
+            ctx.save_for_backward(t, d, u)
+        axpby(M(h), 0.5, M(out), 0.5, M(out))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        n, f, ft = ctx.shapes
+        g = _as_rows(grad, "grad")
+        dev = g.device
+        if ctx.kind == 0:
+            (t,) = ctx.saved_tensors
+            dt = _new(n, ft, g)
+            abs_bwd(M(g, f, ft), M(t), M(dt), 1.0)
+            return g[:, :f], dt, None, None
+        dh = _new(n, f, g)
+        axpby(M(g), 0.5, None, 0.0, M(dh))
+        if ctx.kind == 1:
+            (t,) = ctx.saved_tensors
+            dt = _new(n, ft, g)
+            abs_bwd(M(g), M(t), M(dt), 0.5)
+            return dh, dt, None, None
+        t, d, u = ctx.saved_tensors
+        du = _new(n, f, g)
+        relu_bwd(M(dh), M(u), M(du))                      # 0.5 * g where t D > 0
+        dt = _new(n, ft, g)
+        sgemm(False, True, n, ft, f, du.data_ptr(), f, d.data_ptr(), d.stride(0), dt.data_ptr(), ft, dev)
+        dd = torch.empty((ft, f), dtype=torch.float32, device=dev)
+        sgemm(True, False, ft, f, n, t.data_ptr(), t.stride(0), du.data_ptr(), f, dd.data_ptr(), f, dev, split_k=True)
+        return dh, dt, dd, None
+
+
+# ----------------------------------------------------------------------------
+# DistMult decoder  (decoder.py:19-23)
+# ----------------------------------------------------------------------------
+class DistMult(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, weight, edge_index, edge_type, sigmoid):
+        lib = _lib.load()
+        z = _as_rows(z, "z")
+        w = _as_rows(weight, "weight").contiguous()
+        require_cuda(edge_index, "edge_index", torch.int64)
+        require_cuda(edge_type, "edge_type", torch.int64)
+        if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_type.numel() != edge_index.size(1):
+            raise RuntimeError("edge_index must be [2,E] and edge_type [E]")
+        if w.size(1) != z.size(1):
+            raise RuntimeError("decoder weight width must equal the embedding width")
+        ei, et = edge_index.contiguous(), edge_type.contiguous()
+        e = ei.size(1)
+        out = torch.empty(e, dtype=torch.float32, device=z.device)
+        _lib.check(lib.gn_distmult_fwd(z.data_ptr(), z.stride(0) if z.size(0) > 1 else z.size(1), z.size(1),
+                                       w.data_ptr(), _ptr(ei[0]) if e else None, _ptr(ei[1]) if e else None,
+                                       _ptr(et) if e else None, e, int(sigmoid), _ptr(out), _stream()),
+                   "gn_distmult_fwd")
+        ctx.sigmoid = bool(sigmoid)
+        ctx.key_tensors = (edge_index, edge_type)
+        ctx.save_for_backward(z, w, out, ei, et)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        from .graph import edge_struct
+        lib = _lib.load()
+        z, w, out, ei, et = ctx.saved_tensors
+        n, d, r, e = z.size(0), z.size(1), w.size(0), ei.size(1)
+        dev = z.device
+        g = grad.contiguous()
+        ldz = z.stride(0) if n > 1 else d
+        coef = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.gn_distmult_coef(_ptr(g), _ptr(out), e, int(ctx.sigmoid), _ptr(coef), _stream()),
+                   "gn_distmult_coef")
+        es = edge_struct(ctx.key_tensors[0], ctx.key_tensors[1], n, r)
+        dz = dw = None
+        if ctx.needs_input_grad[0]:
+            dz = torch.empty((n, d), dtype=torch.float32, device=dev)
+            part = es.node.partial(d)
+            _lib.check(lib.gn_distmult_bwd_z(es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid),
+                                             _ptr(coef), z.data_ptr(), ldz, d, w.data_ptr(), dz.data_ptr(), d,
+                                             _ptr(part), _stream()), "gn_distmult_bwd_z")
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((r, d), dtype=torch.float32, device=dev)
+            part = es.rel.partial(d)
+            _lib.check(lib.gn_distmult_bwd_w(es.rel.ref, _ptr(es.rel_eid), _ptr(es.edge_index[0]) if e else None,
+                                             _ptr(es.edge_index[1]) if e else None, _ptr(coef), z.data_ptr(), ldz, d,
+                                             dw.data_ptr(), _ptr(part), _stream()), "gn_distmult_bwd_w")
+        return dz, dw, None, None, None
+
+
+# ----------------------------------------------------------------------------
+# multi-class decoder  softmax(z[node_list] W)   (decoder.py:38-45)
+# ----------------------------------------------------------------------------
+class MultiClass(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, weight, node_list, softmax):
+        lib = _lib.load()
+        z = _as_rows(z, "z")
+        w = _as_rows(weight, "weight").contiguous()
+        require_cuda(node_list, "node_list", torch.int64)
+        if w.size(0) != z.size(1):
+            raise RuntimeError("decoder weight rows must equal the embedding width")
+        idx = node_list.contiguous().view(-1)
+        m, d, c = idx.numel(), z.size(1), w.size(1)
+        dev = z.device
+        logits = torch.empty((m, c), dtype=torch.float32, device=dev)
+        sgemm(False, False, m, c, d, z.data_ptr(), z.stride(0) if z.size(0) > 1 else d, w.data_ptr(), c,
+              logits.data_ptr(), c, dev, a_rows=idx)
+        if softmax:
+            out = torch.empty_like(logits)
+            _lib.check(lib.gn_softmax_fwd(_ptr(logits), m, c, _ptr(out), _stream()), "gn_softmax_fwd")
+        else:
+            out = logits
+        ctx.softmax = bool(softmax)
+        ctx.key_tensor = node_list
+        ctx.save_for_backward(z, w, out, idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        from .graph import index_struct
+        lib = _lib.load()
+        z, w, out, idx = ctx.saved_tensors
+        n, d, c, m = z.size(0), z.size(1), w.size(1), idx.numel()
+        dev = z.device
+        g = grad.contiguous()
+        ldz = z.stride(0) if n > 1 else d
+        if ctx.softmax:
+            gl = torch.empty_like(g)
+            _lib.check(lib.gn_softmax_bwd(_ptr(out), _ptr(g), m, c, _ptr(gl), _stream()), "gn_softmax_bwd")
+        else:
+            gl = g
+        dz = dw = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((d, c), dtype=torch.float32, device=dev)
+            sgemm(True, False, d, c, m, z.data_ptr(), ldz, gl.data_ptr(), c, dw.data_ptr(), c, dev, a_rows=idx,
+                  split_k=True)
+        if ctx.needs_input_grad[0]:
+            grows = torch.empty((max(m, 1), d), dtype=torch.float32, device=dev)
+            sgemm(False, True, m, d, c, gl.data_ptr(), c, w.data_ptr(), c, grows.data_ptr(), d, dev)
+            st = index_struct(ctx.key_tensor, n)
+            dz = torch.empty((n, d), dtype=torch.float32, device=dev)
+            spmm(st.csr, M(grows), M(dz), d)
+        return dz, dw, None, None
+
+
+# ----------------------------------------------------------------------------
+# fused losses  (GripNet-pose.py:140-142, GripNet-aminer.py:133)
+# ----------------------------------------------------------------------------
+class LinkPredLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, neg):
+        lib = _lib.load()
+        pos = require_cuda(pos, "pos_score", torch.float32).contiguous()
+        neg = require_cuda(neg, "neg_score", torch.float32).contiguous()
+        dev = pos.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        n = max(pos.numel(), neg.numel())
+        ws = _ws(lib.gn_loss_workspace_bytes(n), dev)
+        _lib.check(lib.gn_lp_loss_fwd(_ptr(pos), pos.numel(), _ptr(neg), neg.numel(), EPS, _ptr(loss), _ptr(ws),
+                                      ws.numel(), _stream()), "gn_lp_loss_fwd")
+        ctx.save_for_backward(pos, neg)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad):
+        lib = _lib.load()
+        pos, neg = ctx.saved_tensors
+        g = grad.contiguous().view(1)
+        gp, gn_ = torch.empty_like(pos), torch.empty_like(neg)
+        _lib.check(lib.gn_lp_loss_bwd(_ptr(pos), pos.numel(), _ptr(neg), neg.numel(), EPS, _ptr(g), _ptr(gp),
+                                      _ptr(gn_), _stream()), "gn_lp_loss_bwd")
+        return gp, gn_
+
+
+class NodeClassLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, labels):
+        lib = _lib.load()
+        score = _as_rows(score, "score").contiguous()
+        labels = require_cuda(labels, "labels", torch.int64).contiguous()
+        if labels.numel() != score.size(0):
+            raise RuntimeError("labels must have one entry per score row")
+        dev = score.device
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = _ws(lib.gn_loss_workspace_bytes(score.size(0)), dev)
+        _lib.check(lib.gn_nc_loss_fwd(_ptr(score), score.size(0), score.size(1), _ptr(labels), EPS, _ptr(loss),
+                                      _ptr(ws), ws.numel(), _stream()), "gn_nc_loss_fwd")
+        ctx.save_for_backward(score, labels)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, grad):
+        lib = _lib.load()
+        score, labels = ctx.saved_tensors
+        g = grad.contiguous().view(1)
+        gs = torch.empty_like(score)
+        _lib.check(lib.gn_nc_loss_bwd(_ptr(score), score.size(0), score.size(1), _ptr(labels), EPS, _ptr(g),
+                                      _ptr(gs), _stream()), "gn_nc_loss_bwd")
+        return gs, None
+
+
+# ----------------------------------------------------------------------------
+# plain dense product with autograd (encoder.RGCN's input projection)
+# ----------------------------------------------------------------------------
+class MatMul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        x = _as_rows(x, "x")
+        w = _as_rows(w, "w").contiguous()
+        out = _new(x.size(0), w.size(1), x)
+        sgemm(False, False, x.size(0), w.size(1), x.size(1), x.data_ptr(), M(x).ld, w.data_ptr(), w.size(1),
+              out.data_ptr(), w.size(1), x.device)
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, w = ctx.saved_tensors
+        g = _as_rows(grad, "grad")
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _new(x.size(0), x.size(1), x)
+            sgemm(False, True, x.size(0), x.size(1), w.size(1), g.data_ptr(), M(g).ld, w.data_ptr(), w.size(1),
+                  dx.data_ptr(), x.size(1), x.device)
+        if ctx.needs_input_grad[1]:
+            dw = _new(w.size(0), w.size(1), x)
+            sgemm(True, False, w.size(0), w.size(1), x.size(0), x.data_ptr(), M(x).ld, g.data_ptr(), M(g).ld,
+                  dw.data_ptr(), w.size(1), x.device, split_k=True)
+        return dx, dw
+
+
+def matmul(x, w):
+    return MatMul.apply(x, w)

@@ -1,0 +1,228 @@
+/*
+ * gripnet_b200 — C ABI of the B200-native GripNet message-passing hot path.
+ *
+ * The reference (NYXFLOWER/GripNet) is pure Python and has no FFI of its own: its
+ * boundary for this path is the gripnet.layers / gripnet.decoder module API
+ * (SURVEY.md §8b).  This header is the NEW boundary inserted beneath that API.
+ * Each entry point names the reference lines whose arithmetic it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless it says "host"; the caller owns all
+ *    memory (incl. workspaces); the library never allocates or frees device
+ *    memory, keeps no per-call global state and never synchronises the device.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, so
+ *    every call is CUDA-graph capturable.
+ *  - features are fp32 row-major with an explicit leading dimension (`ld*`, in
+ *    floats) so column slices of a concatenated buffer can be read and written
+ *    in place.
+ *  - return value: 0 on success, a negative gn_status otherwise
+ *    (gn_error_string() for text).  No CPU fallback exists: without a CUDA
+ *    device every compute entry point fails with GN_ERR_CUDA.
+ *  - re-entrant: safe to call from the Python main thread (forward) and from
+ *    autograd's device worker thread (backward) concurrently.
+ */
+#ifndef GRIPNET_B200_H
+#define GRIPNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  GN_OK = 0,
+  GN_ERR_ARG = -1,       /* bad size / null pointer / misaligned buffer          */
+  GN_ERR_RANGE = -2,     /* size does not fit the int32 index space (>= 2^31)    */
+  GN_ERR_WORKSPACE = -3, /* workspace too small                                  */
+  GN_ERR_CUDA = -4       /* a CUDA runtime call or kernel launch failed          */
+} gn_status;
+
+int gn_version(void);
+const char* gn_error_string(int status);
+/* number of kernels this library has launched in this process (monotonic) */
+uint64_t gn_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* CSR with a row-split work list ("chunks") for load-balanced, atomic-free   */
+/* row reductions.  All arrays are device pointers.                           */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_rows;          /* output rows                                           */
+  int32_t n_cols;          /* rows of the gathered operand                           */
+  int32_t nnz;             /* stored entries (host copy; may be an upper bound)      */
+  int32_t chunk_len;       /* max entries per chunk                                  */
+  int32_t n_chunks;        /* chunks to launch (exact or an upper bound)             */
+  int32_t _pad;
+  const int32_t* rowptr;   /* [n_rows+1]                                             */
+  const int32_t* col;      /* [nnz] gathered-row index                               */
+  const float* val;        /* [nnz] per-entry coefficient, or NULL for all-ones      */
+  const int32_t* chunk_ptr;/* [n_rows+1] first chunk of each row; [n_rows] = total   */
+  const int32_t* chunk_row;/* [n_chunks] row of each chunk                           */
+  const int32_t* chunk_beg;/* [n_chunks] first entry of each chunk                   */
+  int32_t* row_counter;    /* [n_rows] zero-initialised; left zero by every call     */
+} gn_csr;
+
+/* ---- K1: graph preprocessing ------------------------------------------- */
+
+/* Stable counting (LSD radix) sort of int32 keys in [0, 2^key_bits): rowptr by
+ * histogram + exclusive scan, perm[k] = original position of the entry in slot k.
+ * Replaces nothing 1:1 in the reference; it is the building block that turns
+ * edge_index into the dst-sorted CSR and its transpose (north_star item 1). */
+size_t gn_csr_from_keys_workspace_bytes(int64_t n, int32_t n_rows);
+int gn_csr_from_keys(const int32_t* keys, int64_t n, int32_t n_rows,
+                     int32_t* rowptr /*[n_rows+1]*/, int32_t* perm /*[n]*/,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* Row-split work list for a CSR: a row of length L gets max(1, ceil(L/chunk_len))
+ * chunks.  n_chunks_out (device int32) receives the total. */
+size_t gn_build_chunks_workspace_bytes(int32_t n_rows);
+int gn_build_chunks(const int32_t* rowptr, int32_t n_rows, int32_t chunk_len,
+                    int32_t* chunk_ptr /*[n_rows+1]*/, int32_t* chunk_row, int32_t* chunk_beg,
+                    int64_t chunk_capacity, void* ws, size_t ws_bytes, void* stream);
+
+/* GCN normalisation + CSR pair.  Replaces gripnet/layers.py:52-69 (myGCN.norm):
+ * PyG add_remaining_self_loops, scatter_add degree by TARGET, deg^-1/2 (inf->0),
+ * norm_e = (dis[row]*w)*dis[col].
+ *   bipartite == 0: square graph over n_dst (== n_src) nodes, self-loop rewrite.
+ *   bipartite == 1: interGraph's stacked graph (layers.py:363-368) in closed form:
+ *                   rows = targets, cols = sources, deg_t = 1 + sum w, no loop entries.
+ * Outputs (capacity E + n_dst each unless noted):
+ *   aug_src/aug_dst/aug_norm : the reference-order augmented edge list (int64/fp32);
+ *                              may be NULL when only the CSR is wanted
+ *   rowptr/col/val/perm      : dst-sorted CSR  (perm -> position in the augmented list)
+ *   rowptr_t/col_t/val_t/perm_t : src-sorted (transpose) CSR
+ *   deg [n_dst] fp32 weighted in-degree incl. loop, indeg [n_dst] int32 entry count
+ *   counts (device int32[4]) : {E_aug, n_self_loops_removed, 0, 0}                  */
+size_t gn_gcn_prep_workspace_bytes(int64_t n_edges, int32_t n_src, int32_t n_dst);
+int gn_gcn_prep(const int64_t* src, const int64_t* dst, const float* weight /*or NULL*/,
+                int64_t n_edges, int32_t n_src, int32_t n_dst, int bipartite, float fill_value,
+                int64_t* aug_src, int64_t* aug_dst, float* aug_norm,
+                int32_t* rowptr, int32_t* col, float* val, int32_t* perm,
+                int32_t* rowptr_t, int32_t* col_t, float* val_t, int32_t* perm_t,
+                float* deg, int32_t* indeg, int32_t* counts,
+                void* ws, size_t ws_bytes, void* stream);
+
+/* Multi-relational prep.  Replaces the structure implied by gripnet/layers.py:165-189
+ * (relation of edge e = index of the range_list slice containing e; edge_type unused)
+ * and PyG aggr="mean" (joint in-degree over all relations).
+ *   fwd CSR : rows = targets, col = src*n_rel + rel, no val (row scale 1/max(1,c_i))
+ *   bwd CSR : rows = src*n_rel + rel, col = target, val = 1/max(1,c_target)          */
+size_t gn_rgcn_prep_workspace_bytes(int64_t n_edges, int32_t n_nodes, int32_t n_rel);
+int gn_rgcn_prep(const int64_t* src, const int64_t* dst, int64_t n_edges,
+                 const int64_t* range_list /*[n_rel,2]*/, int32_t n_nodes, int32_t n_rel,
+                 int32_t* rowptr, int32_t* col, int32_t* perm, float* inv_cnt /*[n_nodes]*/,
+                 int32_t* rowptr_t /*[n_nodes*n_rel+1]*/, int32_t* col_t, float* val_t, int32_t* perm_t,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* Endpoint CSR of an edge list for the deterministic DistMult backward:
+ * rows = nodes, 2E entries; entry = (other endpoint, relation, edge id).
+ * Also the relation CSR (rows = relations, E entries = edge ids). */
+size_t gn_edge_prep_workspace_bytes(int64_t n_edges, int32_t n_nodes, int32_t n_rel);
+int gn_edge_prep(const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges,
+                 int32_t n_nodes, int32_t n_rel,
+                 int32_t* node_rowptr /*[n_nodes+1]*/, int32_t* ent_other, int32_t* ent_rel, int32_t* ent_eid /*[2E]*/,
+                 int32_t* rel_rowptr /*[n_rel+1]*/, int32_t* rel_eid /*[E]*/,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* CSR of an index list (rows = nodes, entries = positions in the list) for the
+ * deterministic backward of z[node_list] (gripnet/decoder.py:42). */
+size_t gn_index_prep_workspace_bytes(int64_t n, int32_t n_nodes);
+int gn_index_prep(const int64_t* index, int64_t n, int32_t n_nodes,
+                  int32_t* rowptr, int32_t* perm, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K3/K4/K5/K7/K8: SpMM  ---------------------------------------------- */
+/* out[i, 0:F] = act( row_scale[i] * sum_{k in row i} val[k] * x[col[k], 0:F]
+ *                    + bias + addend[i] )
+ * Replaces MessagePassing.propagate + message + update at gripnet/layers.py:92-100
+ * (GCN, aggr="add"), :167 + :191-197 (RGCN, aggr="mean" via row_scale, root term via
+ * addend) and the ReLU at :279/:305/:370.  Backward passes call it with the
+ * transpose CSR.  Warp per chunk, 128-bit gathers, no atomics on data: rows split
+ * over several chunks are combined in a fixed order by the last-arriving warp.
+ * partial: [n_chunks, F] fp32 scratch (may be NULL when no row has > 1 chunk). */
+int gn_spmm(const gn_csr* csr, const float* x, int64_t ldx, int32_t F,
+            const float* row_scale, const float* bias, const float* addend, int64_t ld_addend,
+            int relu, float* out, int64_t ldo, float* partial, void* stream);
+
+/* ---- K2/K6: dense transforms (fp32, CUDA cores)  -------------------------- */
+/* C[b] = epilogue( alpha * op(A[b]) * op(B[b]) ), b in [0,batch):
+ *   op(A) is M x K (transA: stored K x M), op(B) is K x N (transB: stored N x K);
+ *   batch_reduce != 0: a single C = sum_b op(A[b]) op(B[b]);
+ *   a_rows != NULL: row r of the STORED A is fetched from A + a_rows[r]*lda (row gather);
+ *   epilogue: (+ C if accumulate) (+ addend) then zero where relu_mask <= 0.
+ *   split_k > 1 (batch == 1): K is cut in split_k slices whose partial products
+ *   are summed in slice order from `ws` (deterministic); needs split_k*M*N floats.
+ * Replaces torch.matmul at gripnet/layers.py:73, :172, :181, :193, :383 and
+ * gripnet/decoder.py:42, and their autograd transposes. */
+int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
+             const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+             int32_t batch, int64_t strideA, int64_t strideB, int64_t strideC, int batch_reduce,
+             float alpha, int accumulate, const float* addend, int64_t ld_addend,
+             const float* relu_mask, int64_t ld_mask, const int64_t* a_rows,
+             int32_t split_k, float* ws, size_t ws_bytes, void* stream);
+
+/* ---- K9/K10: DistMult decoder  ------------------------------------------- */
+/* score_e = sum_k z[src_e,k] z[dst_e,k] w[rel_e,k]; sigmoid optional.
+ * Replaces gripnet/decoder.py:19-23 (three [E,D] gathers + two muls + sum). */
+int gn_distmult_fwd(const float* z, int64_t ldz, int32_t D, const float* w,
+                    const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges,
+                    int sigmoid, float* out, void* stream);
+/* per-edge upstream coefficient g_e = grad_e * (sigmoid ? s(1-s) : 1) */
+int gn_distmult_coef(const float* grad_out, const float* out, int64_t n_edges, int sigmoid,
+                     float* coef, void* stream);
+/* dz[n] = sum over endpoint entries (other, rel, e) of coef[e] * z[other] .* w[rel]  */
+int gn_distmult_bwd_z(const gn_csr* node_csr, const int32_t* ent_other, const int32_t* ent_rel,
+                      const int32_t* ent_eid, const float* coef, const float* z, int64_t ldz,
+                      int32_t D, const float* w, float* dz, int64_t lddz, float* partial, void* stream);
+/* dw[r] = sum_{e in relation r} coef[e] * z[src_e] .* z[dst_e] */
+int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64_t* src,
+                      const int64_t* dst, const float* coef, const float* z, int64_t ldz,
+                      int32_t D, float* dw, float* partial, void* stream);
+
+/* ---- K11: multi-class decoder pieces  ------------------------------------ */
+/* row softmax over C columns (gripnet/decoder.py:43) and its backward */
+int gn_softmax_fwd(const float* logits, int64_t n, int32_t C, float* out, void* stream);
+int gn_softmax_bwd(const float* out, const float* grad_out, int64_t n, int32_t C, float* grad_logits,
+                   void* stream);
+
+/* ---- elementwise / reductions used by the layer stacks  ------------------- */
+enum { GN_EW_COPY = 0, GN_EW_ABS = 1, GN_EW_RELU = 2, GN_EW_ADD = 3 /* dst += src */ };
+/* dst[i, 0:F] = op(src[i, 0:F])  (torch.cat / torch.abs at layers.py:309, :376) */
+int gn_map2d(int op, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int32_t F,
+             void* stream);
+/* dst = g where y > 0 else 0   (ReLU backward, layers.py:279/305/370) */
+int gn_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, float* dst, int64_t ldd,
+                int64_t n, int32_t F, void* stream);
+/* dst (+)= g * sign(t)         (backward of torch.abs, layers.py:376/379) */
+int gn_abs_bwd(const float* g, int64_t ldg, const float* t, int64_t ldt, float* dst, int64_t ldd,
+               int64_t n, int32_t F, float scale, void* stream);
+/* dst = alpha * a + beta * b  (b may be NULL; dst may alias a or b)
+ * — the (x + u) / 2 mixes of interGraph, layers.py:379/382-384 */
+int gn_axpby(const float* a, int64_t lda, float alpha, const float* b, int64_t ldb, float beta,
+             float* dst, int64_t ldd, int64_t n, int32_t F, void* stream);
+/* out[0:F] = sum_i x[i, 0:F], deterministic two-level reduction; ws >= gn_colsum_workspace_bytes */
+size_t gn_colsum_workspace_bytes(int64_t n, int32_t F);
+int gn_colsum(const float* x, int64_t ldx, int64_t n, int32_t F, float* out, void* ws, size_t ws_bytes,
+              void* stream);
+/* fused link-prediction loss (GripNet-pose.py:140-142):
+ *   loss = -mean(log(pos+eps)) - mean(log(1-neg+eps)); deterministic two-level sum.
+ * backward reads the upstream gradient from DEVICE memory (no host sync). */
+size_t gn_loss_workspace_bytes(int64_t n);
+int gn_lp_loss_fwd(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, float eps,
+                   float* loss /*[1]*/, void* ws, size_t ws_bytes, void* stream);
+int gn_lp_loss_bwd(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, float eps,
+                   const float* grad_loss /*[1]*/, float* grad_pos, float* grad_neg, void* stream);
+/* fused node-classification loss (GripNet-aminer.py:133):
+ *   loss = -mean(log(score[i, label_i] + eps)) */
+int gn_nc_loss_fwd(const float* score, int64_t n, int32_t C, const int64_t* label, float eps,
+                   float* loss /*[1]*/, void* ws, size_t ws_bytes, void* stream);
+int gn_nc_loss_bwd(const float* score, int64_t n, int32_t C, const int64_t* label, float eps,
+                   const float* grad_loss /*[1]*/, float* grad_score, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIPNET_B200_H */
