@@ -199,7 +199,7 @@ def test_multiclass_decoder():
     rs = np.random.RandomState(4)
     for n, D, C, m in [(50, 288, 8, 30), (40, 32, 5, 60), (10, 7, 3, 4)]:
         z = torch.randn(n, D, dtype=torch.float64)
-        w = torch.randn(D, C, dtype=torch.float64)
+        w = torch.randn(D, C, dtype=torch.float64) / np.sqrt(D)   # keeps the softmax out of saturation
         idx = torch.from_numpy(rs.randint(0, n, m))          # duplicates allowed
         for sm in (True, False):
             zr, wr = z.clone().requires_grad_(True), w.clone().requires_grad_(True)
