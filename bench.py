@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""GripNet hot-path benchmark: fwd+bwd edges/s per epoch on the pose-0-shaped synthetic supergraph.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+
+One "step" = one training epoch's forward + loss + backward over the whole supergraph
+(the reference trains full-batch, GripNet-pose.py:113-144; optimiser excluded).
+edges/s = E_epoch / t_step with E_epoch = 2*E_gg + E_gd + E_dd + 2*E_dd = 4 081 044 input edges.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs in HBM, step replayed
+from a CUDA graph); `e2e` = the same step driven with HOST buffers: the epoch's negative edges are
+copied from pinned host memory each step and the loss + scores are read back (what the reference
+loop moves per epoch, GripNet-pose.py:131,148-164).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "GripNet fwd+bwd edges/sec per epoch (pose-0 shape)"
+UNIT = "edges/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port (reference semantics, torch-CPU, all host threads)
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, state_dict=None):
+    """Time the reference's CPU path (oracle/port.py: index_select -> message -> index_add + autograd)."""
+    from gripnet_b200.synthetic import pose_edges_per_epoch, pose_graph
+    from oracle import port, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = pose_graph()
+    if state_dict is None:
+        p = synth.pose_params(g, bias_jitter=False)
+    else:
+        p = {k: v.detach().cpu().clone() for k, v in state_dict.items()}
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    cache = {}
+    times = []
+    for i in range(warmup + steps):
+        for v in p.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        loss, _, _, _ = port.pose_forward(p, g, cache)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    e_epoch = pose_edges_per_epoch(g)
+    t = sum(times) / len(times)
+    return {"value": e_epoch / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} full pose-0 epochs (fwd+loss+bwd, {e_epoch} edges each) after {warmup} warm-up, "
+                      f"mean {t * 1e3:.0f} ms/epoch",
+            "ms_per_step": t * 1e3, "loss": float(loss)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pose-0-shaped synthetic supergraph (n_g=19081,E_gg=1431224,n_d=645,E_gd=18596,"
+                               "R=16,E_dd=400000), GripNet-pose model, fwd+loss+bwd on host cores"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) >= 9:
+                self.rows.append(f)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def timed_steps(step, n, flush):
+    """Run `step` n times; CUDA events around every step on the current stream, L2 flushed in between."""
+    evs = []
+    for _ in range(n):
+        if flush is not None:
+            flush.zero_()                       # > L2: the next step starts from HBM
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+# ------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch.distributed as dist
+    import gripnet_b200 as gb
+    from gripnet_b200 import ops
+    from gripnet_b200.capture import CapturedStep
+    from gripnet_b200.pipelines import PoseModel, to_device
+    from gripnet_b200.synthetic import pose_edges_per_epoch, pose_graph
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (gripnet_b200 has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload: pose-0-shaped supergraph; at N > 1 every rank owns one pose-0-sized replica of the
+    #      supergraph (weak scaling: per-GPU work fixed); seeds differ per rank.
+    g = pose_graph(seed=1111 + rank)
+    e_epoch = pose_edges_per_epoch(g)
+    torch.manual_seed(1111)
+    model = PoseModel(g["n_g"], g["n_d"], g["n_rel"]).to(dev)
+    data = to_device(g, dev)
+    e_dd = g["dd_edge_index"].shape[1]
+
+    # per-epoch negatives: several pre-sampled sets in pinned host memory (the reference samples on the
+    # host every epoch, utils.py:98-112; sampling itself is outside the hot path)
+    rs = np.random.RandomState(99 + rank)
+    n_sets = 4
+    neg_host = [torch.from_numpy(np.stack([rs.randint(0, g["n_d"], e_dd), rs.randint(0, g["n_d"], e_dd)])
+                                 .astype(np.int64)).pin_memory() for _ in range(n_sets)]
+    neg_static = data["neg_edge_index"].clone()
+
+    def fwd():
+        return model(data, neg_static)
+
+    step = CapturedStep(fwd, model.parameters(), dynamic_inputs=[neg_static], warmup=max(args.warmup, 3))
+    loss_t, z_t, pos_t, neg_t = step.outputs
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    host_scores = torch.empty(2 * e_dd, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K graph replays
+    for _ in range(max(args.warmup, 3)):
+        step.replay()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        t_wall0 = time.perf_counter()
+        times = timed_steps(step.replay, args.steps, flush)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(times)
+
+    # ---- end-to-end: pinned host negatives in, loss + scores out, every step
+    it = [0]
+
+    def e2e_step():
+        neg_static.copy_(neg_host[it[0] % n_sets], non_blocking=True)
+        it[0] += 1
+        step.replay()
+        host_loss.copy_(loss_t.detach().view(1), non_blocking=True)
+        host_scores[:e_dd].copy_(pos_t.detach(), non_blocking=True)
+        host_scores[e_dd:].copy_(neg_t.detach(), non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_times = timed_steps(e2e_step, args.steps, flush)
+    barrier()
+    e2e_ms = sum(e2e_times)
+    final_loss = float(host_loss[0])
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * e_epoch * args.steps / (dev_ms * 1e-3)
+    e2e_value = world * e_epoch * args.steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: the GCN SpMM over the gg graph (4 launches per step),
+    #      timed alone with CUDA events on its own stream, cold L2
+    peaks, peak_src = measured_peaks()
+    gg = model.gg.conv_list[0]._graph
+    F = 16
+    x = torch.randn(gg.n_src, F, device=dev)
+    out = torch.empty(gg.n_dst, F, device=dev)
+    bias = torch.zeros(F, device=dev)
+
+    def spmm_once():
+        ops.spmm(gg.fwd, ops.M(x), ops.M(out), F, bias=bias, relu=True)
+
+    for _ in range(3):
+        spmm_once()
+    k_times = timed_steps(spmm_once, 20, flush)
+    k_ms = statistics.mean(k_times)
+    nnz, n = gg.nnz, gg.n_dst
+    alg_bytes = nnz * (4 + 4 + 4 * F) + n * (8 + 4 * F)      # col + val + gathered row, rowptr + out row
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "spmm_kernel<LPE=4,VEC=4> (GCN SpMM, gg graph, F=16, fwd)",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": None, "algorithmic_bytes": alg_bytes, "us_per_launch": k_ms * 1e3,
+                "peak_source": peak_src,
+                "note": "kernel timed alone, L2 flushed before every launch (burst peak applies); the 1.2 MB "
+                        "gathered operand fits L2, so DRAM traffic is below the algorithmic bytes by design"}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_reference_run(3, 1, {k: v for k, v in model.state_dict().items()})
+            cpu_loss = cpu.pop("loss")
+            cpu.pop("ms_per_step")
+            cpu["loss_check"] = {"cpu_port": cpu_loss, "note": "same parameters and graph, its own fixed negatives"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "pose-0-shaped synthetic supergraph (n_g=19081,E_gg=1431224,n_d=645,E_gd=18596,"
+                                   "R=16,E_dd=400000), GripNet-pose model gg[32,16,16]->gd(64->16|32)->dd RGCN"
+                                   "[48,32]->DistMult(80,16); one step = fwd+loss+bwd of one full-batch epoch",
+                       "edges_per_step": e_epoch, "parallelism": "1 supergraph per GPU" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (write of a 252 MiB buffer, outside the event pair)",
+                       "execution": "whole step replayed from one CUDA graph"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(neg_static.numel() * 8),
+                    "d2h_bytes_per_step": int(4 + 2 * e_dd * 4), "ms_per_step": e2e_ms / args.steps,
+                    "note": "negatives from pinned host memory each step; loss and pos/neg scores read back"},
+            "gpu_launches": int(step.launches_per_replay * args.steps),
+            "launches_per_step": int(step.launches_per_replay),
+            "clocks": clk.summary(), "roofline": roofline, "loss": final_loss,
+            "wall_s_timed_region": t_wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
