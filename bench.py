@@ -101,8 +101,9 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.4)                      # nvidia-smi start-up: first sample before the timed region
         except OSError:
             self.proc = None
         return self
@@ -110,7 +111,7 @@ class ClockSampler:
     def __exit__(self, *exc):
         if self.proc is None:
             return
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
@@ -309,7 +310,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

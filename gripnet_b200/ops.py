@@ -57,24 +57,21 @@ def spmm(csr, x, out, F, row_scale=None, bias=None, addend=None, relu=False):
                            int(relu), out.ptr, out.ld, _ptr(partial), _stream()), "gn_spmm")
 
 
-_SPLITK_TARGET = 148 * 2
-
-
 def sgemm(ta, tb, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, device, batch=1, sa=0, sb=0, sc=0, batch_reduce=False,
-          alpha=1.0, accumulate=False, addend=None, mask=None, a_rows=None, split_k=False):
+          alpha=1.0, accumulate=False, addend=None, mask=None, a_rows=None, split_k=True):
+    """C = epilogue(alpha * op(A) op(B)); the library splits the reduction over CTAs when the
+    output alone cannot fill the GPU (deterministic slice-order sum through ``ws``)."""
     lib = _lib.load()
-    splits, ws, ws_bytes = 1, None, 0
-    if split_k and batch == 1 and k >= 1024:
-        tiles = ((m + 63) // 64) * ((n + 63) // 64)
-        splits = max(1, min(_SPLITK_TARGET // max(tiles, 1), k // 256))
-        if splits > 1:
-            ws = torch.empty(splits * m * n, dtype=torch.float32, device=device)
-            ws_bytes = ws.numel() * 4
+    ws, ws_bytes = None, 0
+    if split_k:
+        ws_bytes = int(lib.gn_sgemm_workspace_bytes(m, n, k, batch, int(batch_reduce)))
+        if ws_bytes:
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=device)
     _lib.check(lib.gn_sgemm(int(ta), int(tb), m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc,
                             int(batch_reduce), float(alpha), int(accumulate),
                             addend.ptr if addend is not None else None, addend.ld if addend is not None else 0,
                             mask.ptr if mask is not None else None, mask.ld if mask is not None else 0,
-                            _ptr(a_rows), splits, _ptr(ws), ws_bytes, _stream()), "gn_sgemm")
+                            _ptr(a_rows), 1 if ws is not None else 0, _ptr(ws), ws_bytes, _stream()), "gn_sgemm")
 
 
 def map2d(op, src, dst):
@@ -185,8 +182,7 @@ class GcnStack(torch.autograd.Function):
             if ctx.needs_input_grad[4 + 2 * (l - 1)]:
                 dw = torch.empty((k, f), dtype=torch.float32, device=dev)
                 # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
-                sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f, dev,
-                      split_k=True)
+                sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f, dev)
                 grads[2 * (l - 1)] = dw
             need_prev = (l > 1) or ctx.needs_input_grad[0]
             if need_prev:
@@ -307,8 +303,7 @@ class RgcnStack(torch.autograd.Function):
             spmm(graph.bwd, dz, M(dy), f)
             if ctx.needs_input_grad[base + 2]:
                 droot = torch.empty((k, f), dtype=torch.float32, device=dev)
-                sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev,
-                      split_k=True)
+                sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev)
                 grads[4 * (l - 1) + 2] = droot
             if ctx.needs_input_grad[base] or ctx.needs_input_grad[base + 1]:
                 # dW[r] = H_{l-1}^T dY[:, r, :]
@@ -410,7 +405,7 @@ class InterTail(torch.autograd.Function):
         dt = _new(n, ft, g)
         sgemm(False, True, n, ft, f, du.data_ptr(), f, d.data_ptr(), d.stride(0), dt.data_ptr(), ft, dev)
         dd = torch.empty((ft, f), dtype=torch.float32, device=dev)
-        sgemm(True, False, ft, f, n, t.data_ptr(), t.stride(0), du.data_ptr(), f, dd.data_ptr(), f, dev, split_k=True)
+        sgemm(True, False, ft, f, n, t.data_ptr(), t.stride(0), du.data_ptr(), f, dd.data_ptr(), f, dev)
         return dh, dt, dd, None
 
 
@@ -515,8 +510,7 @@ class MultiClass(torch.autograd.Function):
         dz = dw = None
         if ctx.needs_input_grad[1]:
             dw = torch.empty((d, c), dtype=torch.float32, device=dev)
-            sgemm(True, False, d, c, m, z.data_ptr(), ldz, gl.data_ptr(), c, dw.data_ptr(), c, dev, a_rows=idx,
-                  split_k=True)
+            sgemm(True, False, d, c, m, z.data_ptr(), ldz, gl.data_ptr(), c, dw.data_ptr(), c, dev, a_rows=idx)
         if ctx.needs_input_grad[0]:
             grows = torch.empty((max(m, 1), d), dtype=torch.float32, device=dev)
             sgemm(False, True, m, d, c, gl.data_ptr(), c, w.data_ptr(), c, grows.data_ptr(), d, dev)
@@ -608,7 +602,7 @@ class MatMul(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = _new(w.size(0), w.size(1), x)
             sgemm(True, False, w.size(0), w.size(1), x.size(0), x.data_ptr(), M(x).ld, g.data_ptr(), M(g).ld,
-                  dw.data_ptr(), w.size(1), x.device, split_k=True)
+                  dw.data_ptr(), w.size(1), x.device)
         return dx, dw
 
 

@@ -147,16 +147,19 @@ int gn_spmm(const gn_csr* csr, const float* x, int64_t ldx, int32_t F,
             const float* row_scale, const float* bias, const float* addend, int64_t ld_addend,
             int relu, float* out, int64_t ldo, float* partial, void* stream);
 
-/* ---- K2/K6: dense transforms (fp32, CUDA cores)  -------------------------- */
+/* ---- K2/K6: dense transforms (fp32 FFMA, CUDA cores)  --------------------- */
 /* C[b] = epilogue( alpha * op(A[b]) * op(B[b]) ), b in [0,batch):
  *   op(A) is M x K (transA: stored K x M), op(B) is K x N (transB: stored N x K);
  *   batch_reduce != 0: a single C = sum_b op(A[b]) op(B[b]);
  *   a_rows != NULL: row r of the STORED A is fetched from A + a_rows[r]*lda (row gather);
  *   epilogue: (+ C if accumulate) (+ addend) then zero where relu_mask <= 0.
- *   split_k > 1 (batch == 1): K is cut in split_k slices whose partial products
- *   are summed in slice order from `ws` (deterministic); needs split_k*M*N floats.
+ *   split_k != 0: when the output tiles alone cannot fill the GPU, the flattened
+ *   (batch-to-reduce, K) reduction is cut into slices whose partial products are
+ *   summed in slice order from `ws` (deterministic, no atomics); `ws` must hold
+ *   gn_sgemm_workspace_bytes(M, N, K, batch, batch_reduce) bytes (0 = no split).
  * Replaces torch.matmul at gripnet/layers.py:73, :172, :181, :193, :383 and
  * gripnet/decoder.py:42, and their autograd transposes. */
+size_t gn_sgemm_workspace_bytes(int32_t M, int32_t N, int32_t K, int32_t batch, int batch_reduce);
 int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
              const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
              int32_t batch, int64_t strideA, int64_t strideB, int64_t strideC, int batch_reduce,

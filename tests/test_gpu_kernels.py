@@ -105,8 +105,7 @@ def test_sgemm_shapes(ta, tb, m, n, k):
     d = _dev()
     At, Bt = torch.from_numpy(A).to(d), torch.from_numpy(B).to(d)
     C = torch.empty(m, n, device=d)
-    ops.sgemm(ta, tb, m, n, k, At.data_ptr(), A.shape[1], Bt.data_ptr(), B.shape[1], C.data_ptr(), n, d,
-              split_k=True)
+    ops.sgemm(ta, tb, m, n, k, At.data_ptr(), A.shape[1], Bt.data_ptr(), B.shape[1], C.data_ptr(), n, d)
     assert rel_err(C, _sgemm_ref(ta, tb, A, B)) < TOL
 
 
