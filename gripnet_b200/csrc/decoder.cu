@@ -57,8 +57,13 @@ __global__ void distmult_coef_kernel(const float* __restrict__ grad_out, const f
 // backward: row-split segmented reductions (no atomics on data)
 //   MODE 0: rows = nodes,     entry (other, rel, e): coef[e] * z[other] .* w[rel]
 //   MODE 1: rows = relations, entry e:               coef[e] * z[src_e] .* z[dst_e]
+// MODE 0 keeps a per-relation run accumulator t = sum coef * z[other] and multiplies by
+// w[rel] only when the relation changes: edge lists are relation-major in practice
+// (GripNet-pose.py:54-56), a stable sort by node keeps that order inside every row, so
+// the w gather and half of the FMAs drop out.  Any order stays correct.
+// Two entries per slot are in flight per iteration (indices first, then the row gathers).
 // ---------------------------------------------------------------------------
-template <int LPE, int VEC, int MODE>
+template <int LPE, int VEC, int NV, int MODE>
 __global__ void __launch_bounds__(256) distmult_bwd_kernel(const gn_csr csr, const int32_t* __restrict__ ent_a,
                                                            const int32_t* __restrict__ ent_b,
                                                            const int32_t* __restrict__ ent_eid,
@@ -74,46 +79,117 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const gn_csr csr, con
   const int lane = threadIdx.x & 31;
   const int slot = lane / LPE, fl = lane % LPE;
 
-  Vec<VEC> acc[kMaxNV];
+  Vec<VEC> acc[NV], run[NV];
 #pragma unroll
-  for (int v = 0; v < kMaxNV; ++v)
+  for (int v = 0; v < NV; ++v)
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[v].v[i] = 0.f;
+    for (int i = 0; i < VEC; ++i) acc[v].v[i] = run[v].v[i] = 0.f;
+  int cur_rel = -1;
 
-  for (int base = ci.beg; base < ci.end; base += EPI) {
-    const int s = base + slot;
-    if (s < ci.end) {
-      const float* pa;
-      const float* pb;
-      float g;
-      if (MODE == 0) {
-        const int e = __ldg(ent_eid + s);
-        g = __ldg(coef + e);
-        pa = z + int64_t(__ldg(ent_a + s)) * ldz;
-        pb = w + int64_t(__ldg(ent_b + s)) * D;
-      } else {
-        const int e = __ldg(ent_eid + s);
-        g = __ldg(coef + e);
-        pa = z + src[e] * ldz;
-        pb = z + dst[e] * ldz;
-      }
+  auto flush = [&](int rel) {
+    const float* wr = w + int64_t(rel) * D;
 #pragma unroll
-      for (int v = 0; v < kMaxNV; ++v) {
+    for (int v = 0; v < NV; ++v) {
+      const int f = (v * LPE + fl) * VEC;
+      if (f < D) {
+        const Vec<VEC> b = load_vec<VEC>(wr + f);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          acc[v].v[i] = fmaf(run[v].v[i], b.v[i], acc[v].v[i]);
+          run[v].v[i] = 0.f;
+        }
+      }
+    }
+  };
+
+  for (int s0 = ci.beg + slot; s0 < ci.end; s0 += 2 * EPI) {
+    const int s1 = s0 + EPI;
+    const bool has1 = s1 < ci.end;
+    // ---- indices of both entries
+    const int e0 = __ldg(ent_eid + s0);
+    const int e1 = has1 ? __ldg(ent_eid + s1) : 0;
+    const float* pa0;
+    const float* pa1 = z;
+    const float* pb0 = z;
+    const float* pb1 = z;
+    int rel0 = 0, rel1 = 0;
+    if (MODE == 0) {
+      pa0 = z + int64_t(__ldg(ent_a + s0)) * ldz;
+      rel0 = __ldg(ent_b + s0);
+      if (has1) {
+        pa1 = z + int64_t(__ldg(ent_a + s1)) * ldz;
+        rel1 = __ldg(ent_b + s1);
+      }
+    } else {
+      pa0 = z + src[e0] * ldz;
+      pb0 = z + dst[e0] * ldz;
+      if (has1) {
+        pa1 = z + src[e1] * ldz;
+        pb1 = z + dst[e1] * ldz;
+      }
+    }
+    const float g0 = __ldg(coef + e0);
+    const float g1 = has1 ? __ldg(coef + e1) : 0.f;
+    if (MODE == 0) {
+      // ---- gathers of both rows, then the run logic in entry order
+      Vec<VEC> a0[NV], a1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
         const int f = (v * LPE + fl) * VEC;
         if (f < D) {
-          const Vec<VEC> a = load_vec<VEC>(pa + f), b = load_vec<VEC>(pb + f);
+          a0[v] = load_vec<VEC>(pa0 + f);
+          a1[v] = load_vec<VEC>(pa1 + f);
+        }
+      }
+      if (rel0 != cur_rel) {
+        if (cur_rel >= 0) flush(cur_rel);
+        cur_rel = rel0;
+      }
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[v].v[i] = fmaf(g * a.v[i], b.v[i], acc[v].v[i]);
+      for (int v = 0; v < NV; ++v) {
+        const int f = (v * LPE + fl) * VEC;
+        if (f < D) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) run[v].v[i] = fmaf(g0, a0[v].v[i], run[v].v[i]);
+        }
+      }
+      if (has1) {
+        if (rel1 != cur_rel) {
+          flush(cur_rel);
+          cur_rel = rel1;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int f = (v * LPE + fl) * VEC;
+          if (f < D) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) run[v].v[i] = fmaf(g1, a1[v].v[i], run[v].v[i]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int f = (v * LPE + fl) * VEC;
+        if (f < D) {
+          const Vec<VEC> a0 = load_vec<VEC>(pa0 + f), b0 = load_vec<VEC>(pb0 + f);
+          const Vec<VEC> a1 = load_vec<VEC>(pa1 + f), b1 = load_vec<VEC>(pb1 + f);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            acc[v].v[i] = fmaf(g0 * a0.v[i], b0.v[i], acc[v].v[i]);
+            acc[v].v[i] = fmaf(g1 * a1.v[i], b1.v[i], acc[v].v[i]);   // g1 == 0 when the slot has no 2nd entry
+          }
         }
       }
     }
   }
+  if (MODE == 0 && cur_rel >= 0) flush(cur_rel);
 #pragma unroll
-  for (int v = 0; v < kMaxNV; ++v) reduce_slots<LPE, VEC>(acc[v]);
+  for (int v = 0; v < NV; ++v) reduce_slots<LPE, VEC>(acc[v]);
 
   const int row = ci.row;
   auto emit = [&](int, int f, const Vec<VEC>& sum) { store_vec<VEC>(outp + int64_t(row) * ldo + f, sum); };
-  finish_row<LPE, VEC, kMaxNV>(csr, ci, acc, D, partial, emit);
+  finish_row<LPE, VEC, NV>(csr, ci, acc, D, partial, emit);
 }
 
 // ---------------------------------------------------------------------------
@@ -149,18 +225,21 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ y, const float* __r
 }
 
 struct WidthPlan {
-  int vec, lpe;
+  int vec, lpe, nv;
   bool ok;
 };
 
-// lanes-per-entry for a D-wide row with at most kMaxNV vectors per lane
+// lanes-per-entry and vectors-per-lane for a D-wide row (at most kMaxNV vectors per lane)
 inline WidthPlan plan_width(int D, bool can_vec4) {
-  WidthPlan p{can_vec4 ? 4 : 1, 0, true};
+  WidthPlan p{can_vec4 ? 4 : 1, 0, 0, true};
   const int units = (D + p.vec - 1) / p.vec;
   if (units <= 4 * kMaxNV) p.lpe = 4;
-  else if (units <= 8 * kMaxNV) p.lpe = 8;
   else if (units <= 32 * kMaxNV) p.lpe = 32;
   else p.ok = false;
+  if (p.ok) {
+    const int need = (units + p.lpe - 1) / p.lpe;
+    p.nv = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 5 ? 5 : kMaxNV;
+  }
   return p;
 }
 
@@ -175,18 +254,19 @@ static int launch_bwd(const gn_csr& csr, const int32_t* ent_a, const int32_t* en
   const WidthPlan p = plan_width(D, v4);
   if (!p.ok) return GN_ERR_ARG;
   const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
-#define GN_BWD_CASE(L, V)                                                                                         \
-  if (p.lpe == L && p.vec == V) {                                                                                 \
-    GN_LAUNCH((distmult_bwd_kernel<L, V, MODE>), grid, 256, 0, st, csr, ent_a, ent_b, ent_eid, src, dst, coef, z, \
-              ldz, D, w, outp, ldo, partial);                                                                     \
-    return GN_OK;                                                                                                 \
+#define GN_BWD_CASE(L, V, N)                                                                                         \
+  if (p.lpe == L && p.vec == V && p.nv == N) {                                                                       \
+    GN_LAUNCH((distmult_bwd_kernel<L, V, N, MODE>), grid, 256, 0, st, csr, ent_a, ent_b, ent_eid, src, dst, coef, z, \
+              ldz, D, w, outp, ldo, partial);                                                                        \
+    return GN_OK;                                                                                                    \
   }
-  GN_BWD_CASE(4, 4)
-  GN_BWD_CASE(8, 4)
-  GN_BWD_CASE(32, 4)
-  GN_BWD_CASE(4, 1)
-  GN_BWD_CASE(8, 1)
-  GN_BWD_CASE(32, 1)
+#define GN_BWD_CASES(L, V) GN_BWD_CASE(L, V, 1) GN_BWD_CASE(L, V, 2) GN_BWD_CASE(L, V, 4) GN_BWD_CASE(L, V, 5) \
+  GN_BWD_CASE(L, V, 8)
+  GN_BWD_CASES(4, 4)
+  GN_BWD_CASES(32, 4)
+  GN_BWD_CASES(4, 1)
+  GN_BWD_CASES(32, 1)
+#undef GN_BWD_CASES
 #undef GN_BWD_CASE
   return GN_ERR_ARG;
 }

@@ -17,7 +17,7 @@
 
 namespace gn {
 
-constexpr int BK = 16;
+constexpr int kBK = 16;         // default k-tile depth
 constexpr int kGemmThreads = 256;
 constexpr int kTargetCtas = 148 * 2;
 constexpr int kMaxSplits = 128;
@@ -33,7 +33,7 @@ struct GemmParams {
   const float* addend; int64_t ldd;
   const float* mask; int64_t ldm;
   const int64_t* a_rows;
-  int kt;              // k-tiles per batch entry: ceil(K / BK)
+  int kt;              // k-tiles per batch entry: ceil(K / bk)
   int iters;           // flattened reduction length: (batch_reduce ? batch : 1) * kt
   int splits;          // CTAs along the reduction
   int iters_per_split;
@@ -42,8 +42,8 @@ struct GemmParams {
 };
 
 struct GemmPlan {
-  int cfg;      // 0: 64x64  1: 128x32  2: 128x16  3: 32x32
-  int bm, bn;
+  int cfg;      // 0: 64x64  1: 128x32  2: 128x16  3: 32x32  4: 32x32 with a 64-deep k-tile
+  int bm, bn, bk;
   int splits, iters_per_split, iters, kt;
   int batch_indep;
 };
@@ -59,7 +59,9 @@ static GemmPlan make_plan(int M, int N, int K, int batch, int batch_reduce, int 
   } else {
     pl.cfg = 0; pl.bm = 64; pl.bn = 64;
   }
-  pl.kt = int(ceil_div(K, BK));
+  pl.bk = kBK;
+  if (pl.cfg == 3 && K >= 256) { pl.cfg = 4; pl.bk = 64; }   // long reductions: fewer, deeper iterations
+  pl.kt = int(ceil_div(K, pl.bk));
   pl.batch_indep = batch_reduce ? 1 : batch;
   pl.iters = (batch_reduce ? batch : 1) * pl.kt;
   const int64_t tiles = ceil_div(M, pl.bm) * ceil_div(N, pl.bn) * pl.batch_indep;
@@ -113,7 +115,7 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, float* C, int 
   }
 }
 
-template <bool TA, bool TB, int BM, int BN, int TM, int TN>
+template <bool TA, bool TB, int BM, int BN, int TM, int TN, int BK>
 __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(const GemmParams p) {
   constexpr int NTX = BN / TN;
   static_assert((BM / TM) * NTX == kGemmThreads, "tile / micro-tile mismatch");
@@ -207,22 +209,33 @@ __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(const GemmParams p)
   }
 }
 
-// sum the reduction slices in slice order, then the epilogue
+// sum the reduction slices in a fixed order, then the epilogue.
+// LANES == 1: one thread per output, slices added in slice order.
+// LANES == 32: one warp per output; lane l adds slices l, l+32, ... in order, then a fixed
+// shuffle tree combines the 32 lane sums (deterministic, and short for ~100 slices).
+template <int LANES>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p, int batch_indep) {
-  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t idx = t / LANES;
+  const int lane = int(t % LANES);
   const int64_t mn = int64_t(p.M) * p.N;
   if (idx >= mn * batch_indep) return;
   const int zb = int(idx / mn);
   const int64_t o = idx - int64_t(zb) * mn;
   const float* w = p.ws + int64_t(zb) * p.splits * mn + o;
   float s = 0.f;
-  int z = 0;
-  for (; z + 4 <= p.splits; z += 4) {          // loads issued together, adds kept in slice order
-    const float a = __ldcg(w + int64_t(z) * mn), b = __ldcg(w + int64_t(z + 1) * mn);
-    const float c = __ldcg(w + int64_t(z + 2) * mn), d = __ldcg(w + int64_t(z + 3) * mn);
+  int z = lane;
+  for (; z + 3 * LANES < p.splits; z += 4 * LANES) {   // loads issued together, adds kept in order
+    const float a = __ldcg(w + int64_t(z) * mn), b = __ldcg(w + int64_t(z + LANES) * mn);
+    const float c = __ldcg(w + int64_t(z + 2 * LANES) * mn), d = __ldcg(w + int64_t(z + 3 * LANES) * mn);
     s += a; s += b; s += c; s += d;
   }
-  for (; z < p.splits; ++z) s += __ldcg(w + int64_t(z) * mn);
+  for (; z < p.splits; z += LANES) s += __ldcg(w + int64_t(z) * mn);
+  if (LANES == 32) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+    if (lane != 0) return;
+  }
   const float v[1] = {s};
   epilogue_row<1>(p, p.C + (p.batch_reduce ? 0 : int64_t(zb) * p.sC), int(o / p.N), int(o % p.N), v);
 }
@@ -230,10 +243,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const GemmParams p, 
 template <bool TA, bool TB>
 static int launch_cfg(const GemmPlan& pl, const GemmParams& p, dim3 grid, cudaStream_t st) {
   switch (pl.cfg) {
-    case 0: GN_LAUNCH((sgemm_kernel<TA, TB, 64, 64, 4, 4>), grid, kGemmThreads, 0, st, p); break;
-    case 1: GN_LAUNCH((sgemm_kernel<TA, TB, 128, 32, 4, 4>), grid, kGemmThreads, 0, st, p); break;
-    case 2: GN_LAUNCH((sgemm_kernel<TA, TB, 128, 16, 2, 4>), grid, kGemmThreads, 0, st, p); break;
-    default: GN_LAUNCH((sgemm_kernel<TA, TB, 32, 32, 2, 2>), grid, kGemmThreads, 0, st, p); break;
+    case 0: GN_LAUNCH((sgemm_kernel<TA, TB, 64, 64, 4, 4, 16>), grid, kGemmThreads, 0, st, p); break;
+    case 1: GN_LAUNCH((sgemm_kernel<TA, TB, 128, 32, 4, 4, 16>), grid, kGemmThreads, 0, st, p); break;
+    case 2: GN_LAUNCH((sgemm_kernel<TA, TB, 128, 16, 2, 4, 16>), grid, kGemmThreads, 0, st, p); break;
+    case 3: GN_LAUNCH((sgemm_kernel<TA, TB, 32, 32, 2, 2, 16>), grid, kGemmThreads, 0, st, p); break;
+    default: GN_LAUNCH((sgemm_kernel<TA, TB, 32, 32, 2, 2, 64>), grid, kGemmThreads, 0, st, p); break;
   }
   return GN_OK;
 }
@@ -282,7 +296,11 @@ extern "C" int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
   else GN_CHECK((launch_cfg<true, true>(pl, p, grid, st)));
   if (pl.splits > 1) {
     const int64_t total = int64_t(M) * N * pl.batch_indep;
-    GN_LAUNCH(splitk_reduce_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, p, pl.batch_indep);
+    if (pl.splits >= 16) {
+      GN_LAUNCH(splitk_reduce_kernel<32>, (unsigned)ceil_div(total * 32, 256), 256, 0, st, p, pl.batch_indep);
+    } else {
+      GN_LAUNCH(splitk_reduce_kernel<1>, (unsigned)ceil_div(total, 256), 256, 0, st, p, pl.batch_indep);
+    }
   }
   return GN_OK;
 }

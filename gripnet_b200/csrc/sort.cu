@@ -1,10 +1,10 @@
-// K1 building blocks: exclusive scan, stable LSD radix sort (counting sort per 8-bit
-// digit), CSR row pointers from sorted keys, row-split chunk lists.
+// K1 building blocks: exclusive scan, stable LSD radix sort (counting sort per 8- or
+// 10-bit digit), CSR row pointers from sorted keys, row-split chunk lists.
 //
 // All of it is integer work and fully deterministic: the sort is stable, so slot k
 // of a CSR row holds the row's entries in their original relative order — the
 // bit-exact contract of SURVEY.md §8 a1 (checked against numpy argsort(kind="stable")).
-#include "common.cuh"
+#include "sortkit.cuh"
 
 namespace gn {
 
@@ -122,105 +122,37 @@ int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* tota
 }
 
 // ----------------------------------------------------------------------------
-// stable LSD radix sort, 8 bits per pass
-//   pass = per-tile digit histogram -> exclusive scan (digit-major) -> stable scatter
+// stable LSD radix sort (kernels in sortkit.cuh), 8 or 10 bits per pass
 // ----------------------------------------------------------------------------
-constexpr int kRsBits = 8;
-constexpr int kRsRadix = 1 << kRsBits;
-constexpr int kRsThreads = 256;
-constexpr int kRsWarps = kRsThreads / 32;
-constexpr int kRsItems = 16;                       // per thread
-constexpr int kRsTile = kRsThreads * kRsItems;     // 4096 keys per block
-constexpr int kRsWarpSpan = kRsItems * 32;         // contiguous keys owned by one warp
-
-__global__ void __launch_bounds__(kRsThreads) rs_histogram(const int32_t* __restrict__ keys, int64_t n, int shift,
-                                                           int32_t* __restrict__ hist, int n_tiles) {
-  __shared__ int h[kRsRadix];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const int64_t base = int64_t(blockIdx.x) * kRsTile;
-#pragma unroll
-  for (int i = 0; i < kRsItems; ++i) {
-    int64_t idx = base + int64_t(i) * kRsThreads + threadIdx.x;
-    if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & (kRsRadix - 1)], 1);
-  }
-  __syncthreads();
-  hist[int64_t(threadIdx.x) * n_tiles + blockIdx.x] = h[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(kRsThreads) rs_scatter(const int32_t* __restrict__ keys_in,
-                                                         const int32_t* __restrict__ vals_in,
-                                                         int32_t* __restrict__ keys_out, int32_t* __restrict__ vals_out,
-                                                         int64_t n, int shift, const int32_t* __restrict__ offsets,
-                                                         int n_tiles) {
-  // cnt[w][d]: first the number of digit-d keys in warp w's span, then (after the
-  // fix-up) the global output position of that warp's first digit-d key.
-  __shared__ int cnt[kRsWarps][kRsRadix];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < kRsWarps * kRsRadix; i += kRsThreads) (&cnt[0][0])[i] = 0;
-  __syncthreads();
-
-  const int64_t warp_base = int64_t(blockIdx.x) * kRsTile + int64_t(warp) * kRsWarpSpan;
-  int32_t key[kRsItems];
-  int32_t rank[kRsItems];
-  const unsigned lt_mask = (1u << lane) - 1u;
-#pragma unroll
-  for (int r = 0; r < kRsItems; ++r) {
-    const int64_t idx = warp_base + r * 32 + lane;      // warp owns a contiguous span, visited in order
-    const bool valid = idx < n;
-    key[r] = valid ? keys_in[idx] : 0;
-    const int digit = valid ? ((key[r] >> shift) & (kRsRadix - 1)) : kRsRadix;  // sentinel groups the tail lanes
-    const unsigned peers = __match_any_sync(kFull, digit);
-    int prior = 0;
-    if (valid) prior = cnt[warp][digit];
-    __syncwarp();
-    rank[r] = prior + __popc(peers & lt_mask);
-    if (valid && (peers & lt_mask) == 0) cnt[warp][digit] = prior + __popc(peers);  // lowest peer updates
-    __syncwarp();
-  }
-  __syncthreads();
-  {
-    const int d = threadIdx.x;  // one thread per digit (kRsThreads == kRsRadix)
-    int running = offsets[int64_t(d) * n_tiles + blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < kRsWarps; ++w) {
-      int c = cnt[w][d];
-      cnt[w][d] = running;
-      running += c;
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < kRsItems; ++r) {
-    const int64_t idx = warp_base + r * 32 + lane;
-    if (idx < n) {
-      const int digit = (key[r] >> shift) & (kRsRadix - 1);
-      const int pos = cnt[warp][digit] + rank[r];
-      keys_out[pos] = key[r];
-      vals_out[pos] = vals_in ? vals_in[idx] : int32_t(idx);
-    }
-  }
-}
-
-static_assert(kRsThreads == kRsRadix, "one thread per digit in the fix-up step");
-
 size_t sort_ws_bytes(int64_t n) {
   if (n <= 0) return 256;
-  const int64_t tiles = ceil_div(n, kRsTile);
-  const int64_t hist = tiles * kRsRadix;
+  const int64_t hist = rs_tiles(n) << 10;
   return align_up(size_t(hist) * 4) + scan_ws_bytes(hist) + 2 * align_up(size_t(n) * 4) + 1024;
+}
+
+template <int RB>
+static int sort_pass(const int32_t* src_k, const int32_t* src_v, int32_t* dst_k, int32_t* dst_v, int64_t n, int shift,
+                     int32_t* hist, int64_t tiles, void* scan_ws, size_t scan_bytes, cudaStream_t st) {
+  const PlainKeys ks{src_k};
+  const PairSink sink{dst_k, dst_v, src_v};
+  GN_LAUNCH((rs_histogram<RB, PlainKeys>), (unsigned)tiles, kRsThreads, 0, st, ks, n, shift, hist, (int)tiles);
+  GN_CHECK(exclusive_scan_i32(hist, hist, tiles << RB, nullptr, scan_ws, scan_bytes, st));
+  GN_LAUNCH((rs_scatter<RB, PlainKeys, PairSink>), (unsigned)tiles, kRsThreads, 0, st, ks, sink, n, shift,
+            (const int32_t*)hist, (int)tiles, (int32_t*)nullptr, 0);
+  return GN_OK;
 }
 
 int sort_pairs(const int32_t* keys_in, const int32_t* vals_in, int32_t* keys_out, int32_t* vals_out, int64_t n,
                int key_bits, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (n <= 0) return GN_OK;
   if (n >= (int64_t(1) << 31)) return GN_ERR_RANGE;
-  const int passes = (key_bits + kRsBits - 1) / kRsBits > 0 ? (key_bits + kRsBits - 1) / kRsBits : 1;
-  const int64_t tiles = ceil_div(n, kRsTile);
+  int passes, rb;
+  rs_plan(key_bits, &passes, &rb);
+  const int64_t tiles = rs_tiles(n);
   Arena a(ws, ws_bytes);
-  int32_t* hist = a.take<int32_t>(size_t(tiles) * kRsRadix);
-  int32_t* tk = a.take<int32_t>(size_t(n));
-  int32_t* tv = a.take<int32_t>(size_t(n));
+  int32_t* hist = a.take<int32_t>(size_t(tiles) << rb);
+  int32_t* tk = passes > 1 ? a.take<int32_t>(size_t(n)) : nullptr;
+  int32_t* tv = passes > 1 ? a.take<int32_t>(size_t(n)) : nullptr;
   if (!a.ok()) return GN_ERR_WORKSPACE;
   void* scan_ws = a.base + a.off;
   const size_t scan_bytes = a.cap - a.off;
@@ -231,11 +163,8 @@ int sort_pairs(const int32_t* keys_in, const int32_t* vals_in, int32_t* keys_out
     const bool to_out = ((passes - 1 - p) % 2) == 0;
     int32_t* dst_k = to_out ? keys_out : tk;
     int32_t* dst_v = to_out ? vals_out : tv;
-    const int shift = p * kRsBits;
-    GN_LAUNCH(rs_histogram, (unsigned)tiles, kRsThreads, 0, st, src_k, n, shift, hist, (int)tiles);
-    GN_CHECK(exclusive_scan_i32(hist, hist, tiles * kRsRadix, nullptr, scan_ws, scan_bytes, st));
-    GN_LAUNCH(rs_scatter, (unsigned)tiles, kRsThreads, 0, st, src_k, src_v, dst_k, dst_v, n, shift,
-              (const int32_t*)hist, (int)tiles);
+    if (rb == 8) GN_CHECK(sort_pass<8>(src_k, src_v, dst_k, dst_v, n, p * 8, hist, tiles, scan_ws, scan_bytes, st));
+    else GN_CHECK(sort_pass<10>(src_k, src_v, dst_k, dst_v, n, p * 10, hist, tiles, scan_ws, scan_bytes, st));
     src_k = dst_k;
     src_v = dst_v;
   }
@@ -269,12 +198,13 @@ int rowptr_from_sorted(const int32_t* sorted_keys, int64_t n, int32_t n_rows, in
 // chunk lists
 // ----------------------------------------------------------------------------
 __global__ void chunk_count_kernel(const int32_t* __restrict__ rowptr, int32_t n_rows, int32_t chunk_len,
-                                   int32_t* __restrict__ cnt) {
+                                   int32_t* __restrict__ cnt, int32_t* __restrict__ row_counter) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rows) return;
   const int len = rowptr[r + 1] - rowptr[r];
   const int c = (len + chunk_len - 1) / chunk_len;
   cnt[r] = c > 0 ? c : 1;
+  if (row_counter) row_counter[r] = 0;
 }
 
 __global__ void chunk_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ chunk_ptr,
@@ -291,6 +221,64 @@ __global__ void chunk_fill_kernel(const int32_t* __restrict__ rowptr, const int3
     }
     beg += chunk_len;
   }
+}
+
+// small CSRs (decoder structures rebuilt every epoch): count + scan + fill in ONE block
+constexpr int kChunkOneBlockRows = 8192;
+__global__ void __launch_bounds__(1024) chunk_one_block_kernel(const int32_t* __restrict__ rowptr, int32_t n_rows,
+                                                               int32_t chunk_len, int32_t* __restrict__ chunk_ptr,
+                                                               int32_t* __restrict__ chunk_row,
+                                                               int32_t* __restrict__ chunk_beg, int64_t capacity,
+                                                               int32_t* __restrict__ row_counter) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n_rows; base += 1024) {
+    const int r = base + threadIdx.x;
+    int c = 0, beg = 0;
+    if (r < n_rows) {
+      beg = rowptr[r];
+      const int len = rowptr[r + 1] - beg;
+      c = (len + chunk_len - 1) / chunk_len;
+      if (c < 1) c = 1;
+      if (row_counter) row_counter[r] = 0;
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int w = warp_sums[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(kFull, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    const int c0 = carry + warp_sums[warp] + incl - c;
+    if (r < n_rows) {
+      chunk_ptr[r] = c0;
+      for (int k = 0; k < c; ++k) {
+        if (c0 + k < capacity) {
+          chunk_row[c0 + k] = r;
+          chunk_beg[c0 + k] = beg + k * chunk_len;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c0 + c;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) chunk_ptr[n_rows] = carry;
 }
 
 }  // namespace gn
@@ -316,7 +304,9 @@ const char* gn_error_string(int status) {
 
 size_t gn_csr_from_keys_workspace_bytes(int64_t n, int32_t n_rows) {
   (void)n_rows;
-  return sort_ws_bytes(n) + align_up(size_t(n > 0 ? n : 1) * 4) + 256;
+  const size_t multi = sort_ws_bytes(n) + align_up(size_t(n > 0 ? n : 1) * 4) + 256;
+  const size_t single = rs_single_pass_ws_bytes(n, 10);
+  return multi > single ? multi : single;
 }
 
 int gn_csr_from_keys(const int32_t* keys, int64_t n, int32_t n_rows, int32_t* rowptr, int32_t* perm, void* ws,
@@ -324,26 +314,38 @@ int gn_csr_from_keys(const int32_t* keys, int64_t n, int32_t n_rows, int32_t* ro
   if (n < 0 || n_rows < 0 || rowptr == nullptr || (n > 0 && (keys == nullptr || perm == nullptr))) return GN_ERR_ARG;
   if (n >= (int64_t(1) << 31)) return GN_ERR_RANGE;
   cudaStream_t st = as_stream(stream);
+  const int bits = bits_for(n_rows > 1 ? n_rows : 2);
+  if (bits <= 10) {  // one pass; row pointers fall out of the scanned histogram
+    const PlainKeys ks{keys};
+    const PermSink sink{perm};
+    if (bits <= 8) return rs_single_pass<8>(ks, sink, n, rowptr, n_rows, ws, ws_bytes, st);
+    return rs_single_pass<10>(ks, sink, n, rowptr, n_rows, ws, ws_bytes, st);
+  }
   Arena a(ws, ws_bytes);
   int32_t* sorted = a.take<int32_t>(size_t(n > 0 ? n : 1));
   if (!a.ok()) return GN_ERR_WORKSPACE;
-  GN_CHECK(sort_pairs(keys, nullptr, sorted, perm, n, bits_for(n_rows > 1 ? n_rows : 2), a.base + a.off,
-                      a.cap - a.off, st));
+  GN_CHECK(sort_pairs(keys, nullptr, sorted, perm, n, bits, a.base + a.off, a.cap - a.off, st));
   return rowptr_from_sorted(sorted, n, n_rows, rowptr, st);
 }
 
 size_t gn_build_chunks_workspace_bytes(int32_t n_rows) { return scan_ws_bytes(int64_t(n_rows) + 1) + 256; }
 
 int gn_build_chunks(const int32_t* rowptr, int32_t n_rows, int32_t chunk_len, int32_t* chunk_ptr, int32_t* chunk_row,
-                    int32_t* chunk_beg, int64_t chunk_capacity, void* ws, size_t ws_bytes, void* stream) {
+                    int32_t* chunk_beg, int64_t chunk_capacity, int32_t* row_counter, void* ws, size_t ws_bytes,
+                    void* stream) {
   if (n_rows < 0 || chunk_len <= 0 || rowptr == nullptr || chunk_ptr == nullptr) return GN_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   if (n_rows == 0) {
     if (cudaMemsetAsync(chunk_ptr, 0, sizeof(int32_t), st) != cudaSuccess) return GN_ERR_CUDA;
     return GN_OK;
   }
+  if (n_rows <= kChunkOneBlockRows) {
+    GN_LAUNCH(chunk_one_block_kernel, 1, 1024, 0, st, rowptr, n_rows, chunk_len, chunk_ptr, chunk_row, chunk_beg,
+              chunk_capacity, row_counter);
+    return GN_OK;
+  }
   const unsigned grid = (unsigned)ceil_div(n_rows, 256);
-  GN_LAUNCH(chunk_count_kernel, grid, 256, 0, st, rowptr, n_rows, chunk_len, chunk_ptr);
+  GN_LAUNCH(chunk_count_kernel, grid, 256, 0, st, rowptr, n_rows, chunk_len, chunk_ptr, row_counter);
   GN_CHECK(exclusive_scan_i32(chunk_ptr, chunk_ptr, n_rows, chunk_ptr + n_rows, ws, ws_bytes, st));
   GN_LAUNCH(chunk_fill_kernel, grid, 256, 0, st, rowptr, (const int32_t*)chunk_ptr, n_rows, chunk_len, chunk_row,
             chunk_beg, chunk_capacity);

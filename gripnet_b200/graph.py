@@ -61,11 +61,11 @@ class Csr:
         self.chunk_ptr = torch.empty(self.n_rows + 1, dtype=torch.int32, device=dev)
         self.chunk_row = torch.empty(cap, dtype=torch.int32, device=dev)
         self.chunk_beg = torch.empty(cap, dtype=torch.int32, device=dev)
-        self.row_counter = torch.zeros(max(self.n_rows, 1), dtype=torch.int32, device=dev)
+        self.row_counter = torch.empty(max(self.n_rows, 1), dtype=torch.int32, device=dev)   # zeroed by the kernel
         ws = _ws(lib.gn_build_chunks_workspace_bytes(self.n_rows), dev)
         _lib.check(lib.gn_build_chunks(_ptr(rowptr), self.n_rows, self.chunk_len, _ptr(self.chunk_ptr),
-                                       _ptr(self.chunk_row), _ptr(self.chunk_beg), cap, _ptr(ws), ws.numel(),
-                                       _stream()), "gn_build_chunks")
+                                       _ptr(self.chunk_row), _ptr(self.chunk_beg), cap, _ptr(self.row_counter),
+                                       _ptr(ws), ws.numel(), _stream()), "gn_build_chunks")
         if exact:   # one host read at graph-build time (never inside a captured step)
             self.n_chunks = int(self.chunk_ptr[self.n_rows].item()) if self.n_rows > 0 else 0
         else:
@@ -194,7 +194,12 @@ class RgcnGraph:
 
 
 class EdgeStruct:
-    """Endpoint CSR + relation CSR of an edge list (deterministic DistMult backward)."""
+    """Endpoint CSR of an edge list (deterministic DistMult backward w.r.t. z).
+
+    The relation CSR (backward w.r.t. the decoder weight) depends on ``edge_type`` only and is
+    cached separately (``rel_struct``), so positive and negative lists that share their types —
+    as in ``GripNet-pose.py:131-138`` — build it once.
+    """
 
     def __init__(self, edge_index, edge_type, n_nodes, n_rel, exact):
         lib = _lib.load()
@@ -210,15 +215,12 @@ class EdgeStruct:
         self.ent_other = torch.empty(max(2 * E, 1), **i32)
         self.ent_rel = torch.empty(max(2 * E, 1), **i32)
         self.ent_eid = torch.empty(max(2 * E, 1), **i32)
-        rel_rowptr = torch.empty(n_rel + 1, **i32)
-        self.rel_eid = torch.empty(max(E, 1), **i32)
         ws = _ws(lib.gn_edge_prep_workspace_bytes(E, n_nodes, n_rel), dev)
         _lib.check(lib.gn_edge_prep(_ptr(ei[0]) if E else None, _ptr(ei[1]) if E else None, _ptr(et) if E else None,
                                     E, n_nodes, n_rel, _ptr(node_rowptr), _ptr(self.ent_other), _ptr(self.ent_rel),
-                                    _ptr(self.ent_eid), _ptr(rel_rowptr), _ptr(self.rel_eid), _ptr(ws), ws.numel(),
+                                    _ptr(self.ent_eid), None, None, _ptr(ws), ws.numel(),
                                     _stream()), "gn_edge_prep")
         self.node = Csr(node_rowptr, self.ent_other, None, n_nodes, n_nodes, 2 * E, exact=exact)
-        self.rel = Csr(rel_rowptr, self.rel_eid, None, n_rel, max(E, 1), E, exact=exact)
 
 
 class IndexStruct:
@@ -296,6 +298,13 @@ def edge_struct(edge_index, edge_type, n_nodes, n_rel):
     exact = not _capturing()
     return _cache.get(key, (edge_index, edge_type),
                       lambda: EdgeStruct(edge_index, edge_type, n_nodes, n_rel, exact))
+
+
+def rel_struct(edge_type, n_rel):
+    """Relation CSR of an edge-type list: row r lists the edge ids of relation r."""
+    key = ("rel", _Cache.tkey(edge_type), n_rel)
+    exact = not _capturing()
+    return _cache.get(key, (edge_type,), lambda: IndexStruct(edge_type, n_rel, exact))
 
 
 def index_struct(index, n_nodes):

@@ -438,7 +438,7 @@ class DistMult(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
-        from .graph import edge_struct
+        from .graph import edge_struct, rel_struct
         lib = _lib.load()
         z, w, out, ei, et = ctx.saved_tensors
         n, d, r, e = z.size(0), z.size(1), w.size(0), ei.size(1)
@@ -448,19 +448,20 @@ class DistMult(torch.autograd.Function):
         coef = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
         _lib.check(lib.gn_distmult_coef(_ptr(g), _ptr(out), e, int(ctx.sigmoid), _ptr(coef), _stream()),
                    "gn_distmult_coef")
-        es = edge_struct(ctx.key_tensors[0], ctx.key_tensors[1], n, r)
         dz = dw = None
         if ctx.needs_input_grad[0]:
+            es = edge_struct(ctx.key_tensors[0], ctx.key_tensors[1], n, r)
             dz = torch.empty((n, d), dtype=torch.float32, device=dev)
             part = es.node.partial(d)
             _lib.check(lib.gn_distmult_bwd_z(es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid),
                                              _ptr(coef), z.data_ptr(), ldz, d, w.data_ptr(), dz.data_ptr(), d,
                                              _ptr(part), _stream()), "gn_distmult_bwd_z")
         if ctx.needs_input_grad[1]:
+            rs = rel_struct(ctx.key_tensors[1], r)
             dw = torch.empty((r, d), dtype=torch.float32, device=dev)
-            part = es.rel.partial(d)
-            _lib.check(lib.gn_distmult_bwd_w(es.rel.ref, _ptr(es.rel_eid), _ptr(es.edge_index[0]) if e else None,
-                                             _ptr(es.edge_index[1]) if e else None, _ptr(coef), z.data_ptr(), ldz, d,
+            part = rs.csr.partial(d)
+            _lib.check(lib.gn_distmult_bwd_w(rs.csr.ref, _ptr(rs.perm), _ptr(ei[0]) if e else None,
+                                             _ptr(ei[1]) if e else None, _ptr(coef), z.data_ptr(), ldz, d,
                                              dw.data_ptr(), _ptr(part), _stream()), "gn_distmult_bwd_w")
         return dz, dw, None, None, None
 

@@ -82,7 +82,8 @@ int gn_csr_from_keys(const int32_t* keys, int64_t n, int32_t n_rows,
 size_t gn_build_chunks_workspace_bytes(int32_t n_rows);
 int gn_build_chunks(const int32_t* rowptr, int32_t n_rows, int32_t chunk_len,
                     int32_t* chunk_ptr /*[n_rows+1]*/, int32_t* chunk_row, int32_t* chunk_beg,
-                    int64_t chunk_capacity, void* ws, size_t ws_bytes, void* stream);
+                    int64_t chunk_capacity, int32_t* row_counter /*[n_rows] zeroed here, or NULL*/,
+                    void* ws, size_t ws_bytes, void* stream);
 
 /* GCN normalisation + CSR pair.  Replaces gripnet/layers.py:52-69 (myGCN.norm):
  * PyG add_remaining_self_loops, scatter_add degree by TARGET, deg^-1/2 (inf->0),
@@ -120,7 +121,9 @@ int gn_rgcn_prep(const int64_t* src, const int64_t* dst, int64_t n_edges,
 
 /* Endpoint CSR of an edge list for the deterministic DistMult backward:
  * rows = nodes, 2E entries; entry = (other endpoint, relation, edge id).
- * Also the relation CSR (rows = relations, E entries = edge ids). */
+ * Also the relation CSR (rows = relations, E entries = edge ids); pass
+ * rel_rowptr == NULL to skip it (it depends on etype only: gn_index_prep(etype)
+ * builds the same structure once for every edge list that shares the types). */
 size_t gn_edge_prep_workspace_bytes(int64_t n_edges, int32_t n_nodes, int32_t n_rel);
 int gn_edge_prep(const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges,
                  int32_t n_nodes, int32_t n_rel,

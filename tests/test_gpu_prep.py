@@ -158,10 +158,13 @@ def test_rgcn_prep():
         RgcnGraph(torch.from_numpy(ei).to(_dev()), torch.tensor([[0, 10], [20, e]]).to(_dev()), n, 2)
 
 
-def test_edge_and_index_prep():
+@pytest.mark.parametrize("n,r,e", [(120, 7, 4000), (645, 16, 50000), (1024, 3, 9000), (1500, 300, 20000),
+                                   (70000, 2, 30000), (5, 1, 0)])
+def test_edge_and_index_prep(n, r, e):
+    """Endpoint CSR / relation CSR / index CSR, bit-exact vs a stable argsort.  Sizes cover the
+    single-pass path (<= 1024 rows, 8- and 10-bit digits) and the multi-pass radix sort."""
     from gripnet_b200.graph import EdgeStruct, IndexStruct
     rs = np.random.RandomState(9)
-    n, r, e = 120, 7, 4000
     ei = rs.randint(0, n, size=(2, e))
     et = rs.randint(0, r, size=e)
     es = EdgeStruct(torch.from_numpy(ei).to(_dev()), torch.from_numpy(et).to(_dev()), n, r, exact=True)
@@ -173,20 +176,24 @@ def test_edge_and_index_prep():
     assert np.array_equal(es.ent_other[: 2 * e].cpu().numpy(), other)
     assert np.array_equal(es.ent_eid[: 2 * e].cpu().numpy(), eid)
     assert np.array_equal(es.ent_rel[: 2 * e].cpu().numpy(), et[eid])
+    rel = IndexStruct(torch.from_numpy(et).to(_dev()), r)
     rp_r, perm_r = port.csr_from_edges(et, r)
-    assert np.array_equal(es.rel.rowptr.cpu().numpy(), rp_r)
-    assert np.array_equal(es.rel_eid[:e].cpu().numpy(), perm_r)
-    idx = rs.randint(0, n, size=300)
+    assert np.array_equal(rel.csr.rowptr.cpu().numpy(), rp_r)
+    assert np.array_equal(rel.perm[:e].cpu().numpy(), perm_r)
+    m = min(300, e)
+    idx = rs.randint(0, n, size=m)
     st = IndexStruct(torch.from_numpy(idx).to(_dev()), n)
     rp_i, perm_i = port.csr_from_edges(idx, n)
-    assert np.array_equal(st.csr.rowptr.cpu().numpy(), rp_i) and np.array_equal(st.perm[:300].cpu().numpy(), perm_i)
+    assert np.array_equal(st.csr.rowptr.cpu().numpy(), rp_i) and np.array_equal(st.perm[:m].cpu().numpy(), perm_i)
+    assert int(st.csr.row_counter.abs().sum()) == 0 and int(es.node.row_counter.abs().sum()) == 0
 
 
+@pytest.mark.parametrize("n_rows", [400, 3000, 20000])       # one-block builder (<= 8192 rows) and the scan path
 @pytest.mark.parametrize("chunk_len", [32, 64, 1024])
-def test_chunk_list_covers_every_entry_once(chunk_len):
+def test_chunk_list_covers_every_entry_once(chunk_len, n_rows):
     from gripnet_b200.graph import Csr
     rs = np.random.RandomState(1)
-    lens = np.concatenate([rs.randint(0, 50, 400), [0, 0, 5000, 33, 32, 31, 1]])
+    lens = np.concatenate([rs.randint(0, 50, n_rows), [0, 0, 5000, 33, 32, 31, 1]])
     rowptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
     nnz = int(rowptr[-1])
     csr = Csr(torch.from_numpy(rowptr).to(_dev()), torch.zeros(nnz, dtype=torch.int32, device=_dev()), None,
