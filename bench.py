@@ -36,13 +36,15 @@ L2_BYTES = 126 * 1024 * 1024
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port (reference semantics, torch-CPU, all host threads)
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, state_dict=None):
-    """Time the reference's CPU path (oracle/port.py: index_select -> message -> index_add + autograd)."""
-    from gripnet_b200.synthetic import pose_edges_per_epoch, pose_graph
+def cpu_reference_run(steps, warmup, state_dict=None, scale=1, budget_s=100.0):
+    """Time the reference's CPU path (oracle/port.py: index_select -> message -> index_add + autograd) on the
+    pose-shaped supergraph (scaled `scale`-fold like the CUDA arm at N = scale GPUs).  Full epochs; at most
+    `steps` of them and at most ~`budget_s` seconds of timed work (never fewer than 2)."""
+    from gripnet_b200.synthetic import pose_edges_per_epoch, pose_graph_scaled
     from oracle import port, synth
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g = pose_graph()
+    g = pose_graph_scaled(scale)
     if state_dict is None:
         p = synth.pose_params(g, bias_jitter=False)
     else:
@@ -50,7 +52,8 @@ def cpu_reference_run(steps, warmup, state_dict=None):
     p = {k: v.requires_grad_(True) for k, v in p.items()}
     cache = {}
     times = []
-    for i in range(warmup + steps):
+    i = 0
+    while True:
         for v in p.values():
             v.grad = None
         t0 = time.perf_counter()
@@ -59,25 +62,30 @@ def cpu_reference_run(steps, warmup, state_dict=None):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
+        i += 1
+        if len(times) >= steps or (len(times) >= 2 and sum(times) + dt > budget_s):
+            break
     e_epoch = pose_edges_per_epoch(g)
     t = sum(times) / len(times)
     return {"value": e_epoch / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} full pose-0 epochs (fwd+loss+bwd, {e_epoch} edges each) after {warmup} warm-up, "
-                      f"mean {t * 1e3:.0f} ms/epoch",
-            "ms_per_step": t * 1e3, "loss": float(loss)}
+            "sample": f"{len(times)} full pose-shaped epochs x{scale} (fwd+loss+bwd, {e_epoch} edges each) after "
+                      f"{warmup} warm-up, mean {t * 1e3:.0f} ms/epoch",
+            "ms_per_step": t * 1e3, "loss": float(loss.detach()), "steps_run": len(times)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference_run(args.steps, max(args.warmup, 1))
+    scale = max(1, int(os.environ.get("WORLD_SIZE", args.gpus)))
+    r = cpu_reference_run(args.steps, max(args.warmup, 1), scale=scale)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "steps": r["steps_run"], "requested_steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pose-0-shaped synthetic supergraph (n_g=19081,E_gg=1431224,n_d=645,E_gd=18596,"
-                               "R=16,E_dd=400000), GripNet-pose model, fwd+loss+bwd on host cores"},
+        "config": {"workload": (POSE_DESC if scale == 1 else f"pose-shaped synthetic supergraph scaled x{scale}, "
+                                "same model") + "; fwd+loss+bwd on host cores (oracle port of the reference path)"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -160,13 +168,121 @@ def timed_steps(step, n, flush):
 # ------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------
+POSE_DESC = ("pose-0-shaped synthetic supergraph (n_g=19081,E_gg=1431224,n_d=645,E_gd=18596,R=16,E_dd=400000), "
+             "GripNet-pose model gg[32,16,16]->gd(64->16|32)->dd RGCN[48,32]->DistMult(80,16); one step = "
+             "fwd+loss+bwd of one full-batch epoch")
+
+
+def build_pose(args, world, rank, dev, dctx):
+    """pose-0 at N=1; at N>1 the pose-shaped supergraph scaled N-fold (weak scaling) and destination-
+    partitioned over the N ranks: every rank owns 1/N of the rows of every supervertex and
+    1/N of the decoder edge lists; halo rows move by NCCL all-gather."""
+    from gripnet_b200.pipelines import PoseModel, shard_pose, to_device
+    from gripnet_b200.synthetic import pose_edges_per_epoch, pose_graph_scaled
+    g = pose_graph_scaled(world, seed=1111)
+    e_epoch = pose_edges_per_epoch(g)
+    torch.manual_seed(1111)
+    if world == 1:
+        model = PoseModel(g["n_g"], g["n_d"], g["n_rel"]).to(dev)
+        data = to_device(g, dev)
+        neg_static = data["neg_edge_index"].clone()
+        n_d = g["n_d"]
+    else:
+        data = shard_pose(g, dctx, dev)
+        torch.manual_seed(1111 + rank)
+        model = PoseModel(data["n_g"], data["n_d"], g["n_rel"]).to(dev)
+        model.dmt.dist_ctx = dctx
+        _sync_replicated(model, ("gg.embedding", "gd.target_feat"))
+        neg_static = data["neg_edge_index_local"].clone()
+        n_d = g["n_d"]
+    e_loc = neg_static.size(1)
+    rs = np.random.RandomState(99 + rank)
+    n_sets = 4
+    neg_host = [torch.from_numpy(np.stack([rs.randint(0, n_d, e_loc), rs.randint(0, n_d, e_loc)]).astype(np.int64))
+                .pin_memory() for _ in range(n_sets)]
+
+    def fwd():
+        return model(data, neg_static)
+
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    host_scores = torch.empty(2 * e_loc, dtype=torch.float32).pin_memory()
+    it = [0]
+
+    def h2d():
+        neg_static.copy_(neg_host[it[0] % n_sets], non_blocking=True)
+        it[0] += 1
+
+    def d2h(outs):
+        host_loss.copy_(outs[0].detach().view(1), non_blocking=True)
+        host_scores[:e_loc].copy_(outs[2].detach(), non_blocking=True)
+        host_scores[e_loc:].copy_(outs[3].detach(), non_blocking=True)
+
+    desc = POSE_DESC if world == 1 else (
+        f"pose-shaped synthetic supergraph scaled x{world} (n_g={g['n_g']},E_gg={g['gg_edge_index'].shape[1]},"
+        f"n_d={g['n_d']},E_gd={g['gd_edge_index'].shape[1]},R=16,E_dd={g['dd_edge_index'].shape[1]}), same model, "
+        f"destination-partitioned over {world} GPUs")
+    return dict(model=model, fwd=fwd, dynamic=[neg_static], edges=e_epoch, h2d=h2d, d2h=d2h, host_loss=host_loss,
+                h2d_bytes=int(neg_static.numel() * 8), d2h_bytes=int(4 + 2 * e_loc * 4), desc=desc,
+                spmm_graph=lambda: model.gg.conv_list[0]._graph, spmm_f=16,
+                e2e_note="negatives from pinned host memory each step; loss and pos/neg scores read back")
+
+
+def build_chain(args, world, rank, dev, dctx):
+    """BASELINE config 5: ~10 M nodes / ~520 M edges, three supervertices, destination-partitioned."""
+    from gripnet_b200.pipelines import ChainModel, chain_edges_per_epoch, shard_chain
+    from gripnet_b200.synthetic import chain_full, chain_small
+    g = chain_small(dev) if args.workload == "scaled-small" else chain_full(dev)
+    e_epoch = chain_edges_per_epoch(g)
+    if dctx is None:
+        data = dict(g)
+    else:
+        data = shard_chain(g, dctx, dev)
+    torch.manual_seed(1111 + rank)
+    model = ChainModel(data["n_a"], data["n_b"], data["n_c"], g["n_class"]).to(dev)
+    if dctx is not None:
+        model.mcip.dist_ctx = dctx
+        _sync_replicated(model, ("aa.embedding", "ab.target_feat", "bc.target_feat"))
+    labels_static = data["train_node_class"]
+    labels_host = labels_static.cpu().pin_memory()
+    n_lab = labels_static.numel()
+    n_class = g["n_class"]
+    del g
+    torch.cuda.empty_cache()
+
+    def fwd():
+        return model(data)
+
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    host_scores = torch.empty(n_lab * n_class, dtype=torch.float32).pin_memory()
+
+    def h2d():
+        labels_static.copy_(labels_host, non_blocking=True)
+
+    def d2h(outs):
+        host_loss.copy_(outs[0].detach().view(1), non_blocking=True)
+        host_scores.copy_(outs[2].detach().view(-1), non_blocking=True)
+
+    desc = (f"scaled synthetic supergraph chain A->B->C (R-MAT degrees; 10 M nodes, {e_epoch} edge traversals per "
+            f"forward), ChainModel hid=64, node classification on C, destination-partitioned over {world} GPU(s)")
+    return dict(model=model, fwd=fwd, dynamic=[], edges=e_epoch, h2d=h2d, d2h=d2h, host_loss=host_loss,
+                h2d_bytes=int(n_lab * 8), d2h_bytes=int(4 + n_lab * n_class * 4), desc=desc,
+                spmm_graph=lambda: model.aa.conv_list[0]._graph, spmm_f=64,
+                e2e_note="labels from pinned host memory each step; loss and class scores read back")
+
+
+def _sync_replicated(model, row_partitioned):
+    """Replicated parameters must be identical on every rank: broadcast rank 0's."""
+    import torch.distributed as dist
+    for k, v in model.named_parameters():
+        if k not in row_partitioned:
+            dist.broadcast(v.data, src=0)
+
+
 def run_cuda(args):
     import torch.distributed as dist
     import gripnet_b200 as gb
     from gripnet_b200 import ops
     from gripnet_b200.capture import CapturedStep
-    from gripnet_b200.pipelines import PoseModel, to_device
-    from gripnet_b200.synthetic import pose_edges_per_epoch, pose_graph
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -175,41 +291,53 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device (gripnet_b200 has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    dctx = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from gripnet_b200.parallel import DistContext
+        dctx = DistContext()
 
-    # ---- workload: pose-0-shaped supergraph; at N > 1 every rank owns one pose-0-sized replica of the
-    #      supergraph (weak scaling: per-GPU work fixed); seeds differ per rank.
-    g = pose_graph(seed=1111 + rank)
-    e_epoch = pose_edges_per_epoch(g)
-    torch.manual_seed(1111)
-    model = PoseModel(g["n_g"], g["n_d"], g["n_rel"]).to(dev)
-    data = to_device(g, dev)
-    e_dd = g["dd_edge_index"].shape[1]
+    w = (build_pose if args.workload == "pose" else build_chain)(args, world, rank, dev, dctx)
+    model, e_epoch = w["model"], w["edges"]
 
-    # per-epoch negatives: several pre-sampled sets in pinned host memory (the reference samples on the
-    # host every epoch, utils.py:98-112; sampling itself is outside the hot path)
-    rs = np.random.RandomState(99 + rank)
-    n_sets = 4
-    neg_host = [torch.from_numpy(np.stack([rs.randint(0, g["n_d"], e_dd), rs.randint(0, g["n_d"], e_dd)])
-                                 .astype(np.int64)).pin_memory() for _ in range(n_sets)]
-    neg_static = data["neg_edge_index"].clone()
+    # ---- execution: whole step replayed from one CUDA graph (NCCL collectives included when N > 1)
+    execution = "whole step replayed from one CUDA graph"
+    step = None
+    if not args.eager:
+        try:
+            step = CapturedStep(w["fwd"], model.parameters(), dynamic_inputs=w["dynamic"], warmup=max(args.warmup, 3))
+        except Exception as e:  # pragma: no cover - capture of NCCL can be refused by the runtime
+            if world == 1:
+                raise
+            sys.stderr.write(f"bench.py: CUDA-graph capture failed on rank {rank} ({type(e).__name__}: {e}); running eagerly\n")
+            torch.cuda.synchronize()
+            step = None
+    if step is None:
+        execution = "eager launches (no CUDA graph)"
 
-    def fwd():
-        return model(data, neg_static)
+        class _Eager:
+            def __init__(self):
+                self.outputs = None
+                self.launches_per_replay = 0
 
-    step = CapturedStep(fwd, model.parameters(), dynamic_inputs=[neg_static], warmup=max(args.warmup, 3))
-    loss_t, z_t, pos_t, neg_t = step.outputs
+            def replay(self):
+                for p in model.parameters():
+                    p.grad = None
+                before = gb.launch_count()
+                self.outputs = w["fwd"]()
+                self.outputs[0].backward()
+                self.launches_per_replay = gb.launch_count() - before
+                return self.outputs
+        step = _Eager()
+        step.replay()
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
-    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
-    host_scores = torch.empty(2 * e_dd, dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: K graph replays
+    # ---- device-resident timing
     for _ in range(max(args.warmup, 3)):
         step.replay()
     barrier()
@@ -220,16 +348,11 @@ def run_cuda(args):
         t_wall = time.perf_counter() - t_wall0
     dev_ms = sum(times)
 
-    # ---- end-to-end: pinned host negatives in, loss + scores out, every step
-    it = [0]
-
+    # ---- end-to-end: pinned host inputs in, loss + scores out, every step
     def e2e_step():
-        neg_static.copy_(neg_host[it[0] % n_sets], non_blocking=True)
-        it[0] += 1
-        step.replay()
-        host_loss.copy_(loss_t.detach().view(1), non_blocking=True)
-        host_scores[:e_dd].copy_(pos_t.detach(), non_blocking=True)
-        host_scores[e_dd:].copy_(neg_t.detach(), non_blocking=True)
+        w["h2d"]()
+        outs = step.replay()
+        w["d2h"](outs)
 
     for _ in range(3):
         e2e_step()
@@ -237,22 +360,23 @@ def run_cuda(args):
     e2e_times = timed_steps(e2e_step, args.steps, flush)
     barrier()
     e2e_ms = sum(e2e_times)
-    final_loss = float(host_loss[0])
+    final_loss = float(w["host_loss"][0])
 
-    # ---- max over ranks
+    # ---- max over ranks (the same global step runs on every rank: value = global edges / slowest rank)
     if world > 1:
         t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = float(t[0]), float(t[1])
-    value = world * e_epoch * args.steps / (dev_ms * 1e-3)
-    e2e_value = world * e_epoch * args.steps / (e2e_ms * 1e-3)
+    value = e_epoch * args.steps / (dev_ms * 1e-3)
+    e2e_value = e_epoch * args.steps / (e2e_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel: the GCN SpMM over the gg graph (4 launches per step),
-    #      timed alone with CUDA events on its own stream, cold L2
+    # ---- roofline of the dominant kernel: the GCN SpMM over the largest intra-supervertex graph (this
+    #      rank's rows), timed alone with CUDA events on its own stream, cold L2
     peaks, peak_src = measured_peaks()
-    gg = model.gg.conv_list[0]._graph
-    F = 16
-    x = torch.randn(gg.n_src, F, device=dev)
+    gg = w["spmm_graph"]()
+    F = w["spmm_f"]
+    n_cols = gg.fwd.n_cols
+    x = torch.randn(n_cols, F, device=dev)
     out = torch.empty(gg.n_dst, F, device=dev)
     bias = torch.zeros(F, device=dev)
 
@@ -263,37 +387,38 @@ def run_cuda(args):
         spmm_once()
     k_times = timed_steps(spmm_once, 20, flush)
     k_ms = statistics.mean(k_times)
-    nnz, n = gg.nnz, gg.n_dst
+    nnz, n = gg.fwd.nnz, gg.n_dst
     alg_bytes = nnz * (4 + 4 + 4 * F) + n * (8 + 4 * F)      # col + val + gathered row, rowptr + out row
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "spmm_kernel<LPE=4,VEC=4> (GCN SpMM, gg graph, F=16, fwd)",
+    operand_mb = n_cols * F * 4 / 1e6
+    roofline = {"bound": "hbm", "kernel": f"spmm_kernel (GCN SpMM fwd, largest intra-supervertex graph, F={F}, "
+                                          f"{nnz} entries, {n} rows on this rank)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "algorithmic_bytes": alg_bytes, "us_per_launch": k_ms * 1e3,
-                "peak_source": peak_src,
-                "note": "kernel timed alone, L2 flushed before every launch (burst peak applies); the 1.2 MB "
-                        "gathered operand fits L2, so DRAM traffic is below the algorithmic bytes by design"}
+                "traffic": TRAFFIC.get(args.workload if world == 1 else None), "algorithmic_bytes": alg_bytes,
+                "us_per_launch": k_ms * 1e3, "peak_source": peak_src,
+                "note": f"kernel timed alone, L2 flushed before every launch (burst peak applies); gathered operand "
+                        f"is {operand_mb:.1f} MB " + ("(fits the 126 MB L2: DRAM traffic is below the algorithmic "
+                                                      "bytes by design)" if operand_mb < 100 else "(exceeds L2)")}
 
-    line = None
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and args.workload == "pose" and not args.no_cpu_baseline:
             cpu = cpu_reference_run(3, 1, {k: v for k, v in model.state_dict().items()})
             cpu_loss = cpu.pop("loss")
             cpu.pop("ms_per_step")
+            cpu.pop("steps_run")
             cpu["loss_check"] = {"cpu_port": cpu_loss, "note": "same parameters and graph, its own fixed negatives"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "pose-0-shaped synthetic supergraph (n_g=19081,E_gg=1431224,n_d=645,E_gd=18596,"
-                                   "R=16,E_dd=400000), GripNet-pose model gg[32,16,16]->gd(64->16|32)->dd RGCN"
-                                   "[48,32]->DistMult(80,16); one step = fwd+loss+bwd of one full-batch epoch",
-                       "edges_per_step": e_epoch, "parallelism": "1 supergraph per GPU" if world > 1 else "single GPU",
+            "config": {"workload": w["desc"], "edges_per_step": e_epoch,
+                       "parallelism": "single GPU" if world == 1 else
+                       f"destination-partitioned x{world}: NCCL all-gather of SpMM operands, all-reduce of weight grads",
                        "l2": "flushed between timed steps (write of a 252 MiB buffer, outside the event pair)",
-                       "execution": "whole step replayed from one CUDA graph"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(neg_static.numel() * 8),
-                    "d2h_bytes_per_step": int(4 + 2 * e_dd * 4), "ms_per_step": e2e_ms / args.steps,
-                    "note": "negatives from pinned host memory each step; loss and pos/neg scores read back"},
+                       "execution": execution},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": w["h2d_bytes"],
+                    "d2h_bytes_per_step": w["d2h_bytes"], "ms_per_step": e2e_ms / args.steps, "note": w["e2e_note"]},
             "gpu_launches": int(step.launches_per_replay * args.steps),
             "launches_per_step": int(step.launches_per_replay),
             "clocks": clk.summary(), "roofline": roofline, "loss": final_loss,
@@ -307,6 +432,11 @@ def run_cuda(args):
     return 0
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed
+# `ncu --set full` capture of the same command (profiles/), keyed by workload at N=1
+TRAFFIC = {"pose": 13149696}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -314,6 +444,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pose", choices=["pose", "scaled", "scaled-small"],
+                    help="pose: BASELINE metric workload (pose-0 at N=1, scaled N-fold and partitioned at N>1); "
+                         "scaled: BASELINE config 5 (10 M nodes / 520 M edges chain)")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step into a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

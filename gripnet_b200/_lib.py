@@ -35,6 +35,7 @@ SIGNATURES = {
     "gn_launch_count": (C.c_uint64, []),
     "gn_csr_from_keys_workspace_bytes": (_SZ, [_I64, _I32]),
     "gn_csr_from_keys": (_INT, [_P, _I64, _I32, _P, _P, _P, _SZ, _P]),
+    "gn_rowptr_slice": (_INT, [_P, _I32, _I32, _P, _P]),
     "gn_build_chunks_workspace_bytes": (_SZ, [_I32]),
     "gn_build_chunks": (_INT, [_P, _I32, _I32, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
     "gn_gcn_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),

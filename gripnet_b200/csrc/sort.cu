@@ -194,6 +194,13 @@ int rowptr_from_sorted(const int32_t* sorted_keys, int64_t n, int32_t n_rows, in
   return GN_OK;
 }
 
+// rows [r0, r0+n) of a CSR: rebased row pointers (destination-partitioned graphs)
+__global__ void rowptr_slice_kernel(const int32_t* __restrict__ rowptr, int32_t r0, int32_t n_rows,
+                                    int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n_rows) out[i] = rowptr[r0 + i] - rowptr[r0];
+}
+
 // ----------------------------------------------------------------------------
 // chunk lists
 // ----------------------------------------------------------------------------
@@ -326,6 +333,13 @@ int gn_csr_from_keys(const int32_t* keys, int64_t n, int32_t n_rows, int32_t* ro
   if (!a.ok()) return GN_ERR_WORKSPACE;
   GN_CHECK(sort_pairs(keys, nullptr, sorted, perm, n, bits, a.base + a.off, a.cap - a.off, st));
   return rowptr_from_sorted(sorted, n, n_rows, rowptr, st);
+}
+
+int gn_rowptr_slice(const int32_t* rowptr, int32_t r0, int32_t n_rows, int32_t* out, void* stream) {
+  if (!rowptr || !out || r0 < 0 || n_rows < 0) return GN_ERR_ARG;
+  GN_LAUNCH(rowptr_slice_kernel, (unsigned)ceil_div(int64_t(n_rows) + 1, 256), 256, 0, as_stream(stream), rowptr, r0,
+            n_rows, out);
+  return GN_OK;
 }
 
 size_t gn_build_chunks_workspace_bytes(int32_t n_rows) { return scan_ws_bytes(int64_t(n_rows) + 1) + 256; }

@@ -5,6 +5,7 @@ import torch
 from torch.nn import Module, Parameter
 
 from . import ops
+from .parallel import replicated
 
 
 class multiRelaInnerProductDecoder(Module):
@@ -19,10 +20,11 @@ class multiRelaInnerProductDecoder(Module):
         super().__init__()
         self.num_et, self.in_dim = num_et, in_dim
         self.weight = Parameter(torch.empty(num_et, in_dim))
+        self.dist_ctx = None          # set to a parallel.DistContext when edge lists are partitioned over ranks
         self.reset_parameters()
 
     def forward(self, z, edge_index, edge_type, sigmoid=True):
-        return ops.DistMult.apply(z, self.weight, edge_index, edge_type, bool(sigmoid))
+        return ops.DistMult.apply(z, replicated(self.weight, self.dist_ctx), edge_index, edge_type, bool(sigmoid))
 
     def reset_parameters(self):
         with torch.no_grad():
@@ -36,12 +38,13 @@ class multiClassInnerProductDecoder(Module):
         super().__init__()
         self.num_class, self.in_dim = num_class, in_dim
         self.weight = Parameter(torch.empty(in_dim, num_class))
+        self.dist_ctx = None          # set to a parallel.DistContext when node lists are partitioned over ranks
         self.reset_parameters()
 
     def forward(self, z, node_list, softmax=True):
         if not torch.is_tensor(node_list):
             node_list = torch.as_tensor(node_list, dtype=torch.int64, device=z.device)
-        return ops.MultiClass.apply(z, self.weight, node_list, bool(softmax))
+        return ops.MultiClass.apply(z, replicated(self.weight, self.dist_ctx), node_list, bool(softmax))
 
     def reset_parameters(self):
         bound = math.sqrt(6.0 / (self.in_dim + self.num_class))            # decoder.py:47-49

@@ -193,6 +193,64 @@ class RgcnGraph:
         self.bwd = Csr(rowptr_t, col_t, val_t, n_nodes * n_rel, n_nodes, E)
 
 
+def slice_csr(csr, r0, r1, n_cols):
+    """Rows ``[r0, r1)`` of a device CSR as a stand-alone ``Csr`` (own chunk list).
+
+    ``col`` / ``val`` are copies of the corresponding slices of the global arrays (so the global
+    arrays can be freed) and ``rowptr`` is rebased by a kernel: bit-identical to slicing."""
+    lib = _lib.load()
+    n_local = int(r1 - r0)
+    dev = csr.rowptr.device
+    rowptr = torch.empty(n_local + 1, dtype=torch.int32, device=dev)
+    _lib.check(lib.gn_rowptr_slice(_ptr(csr.rowptr), int(r0), n_local, _ptr(rowptr), _stream()), "gn_rowptr_slice")
+    a, b = (int(v) for v in csr.rowptr[[r0, r1]].tolist())          # two host reads at graph-build time
+    col = csr.col[a:b].clone() if b > a else torch.empty(1, dtype=torch.int32, device=dev)
+    val = None
+    if csr.val is not None:
+        val = csr.val[a:b].clone() if b > a else torch.empty(1, dtype=torch.float32, device=dev)
+    return Csr(rowptr, col, val, n_local, n_cols, b - a)
+
+
+class DistGcnGraph:
+    """This rank's rows of a destination-partitioned GCN graph (``parallel.py``).
+
+    ``fwd``: local TARGET rows of the dst-sorted CSR, columns = global source ids (the gathered
+    operand has ``world * b_src`` rows); ``bwd``: local SOURCE rows of the transpose CSR, columns =
+    global target ids.  ``n_src`` / ``n_dst`` are the LOCAL row counts the layer stacks see."""
+
+    def __init__(self, edge_index, spec, edge_weight=None, improved=False, bipartite=False):
+        ctx = spec.ctx
+        g = GcnGraph(edge_index, spec.n_src, spec.n_dst, edge_weight, improved, bipartite)   # replicated prep
+        self.ctx, self.bipartite = ctx, bool(bipartite)
+        self.n_src_global, self.n_dst_global, self.n_edges = spec.n_src, spec.n_dst, g.n_edges
+        self.b_src, self.b_dst = ctx.block(spec.n_src), ctx.block(spec.n_dst)
+        s0, s1 = ctx.bounds(spec.n_src)
+        d0, d1 = ctx.bounds(spec.n_dst)
+        self.src_bounds, self.dst_bounds = (s0, s1), (d0, d1)
+        self.n_src, self.n_dst = s1 - s0, d1 - d0
+        self.fwd = slice_csr(g.fwd, d0, d1, ctx.world * self.b_src)
+        self.bwd = slice_csr(g.bwd, s0, s1, ctx.world * self.b_dst)
+        self.nnz = self.fwd.nnz
+        self.deg, self.indeg = g.deg[d0:d1].clone(), g.indeg[d0:d1].clone()
+
+
+class DistRgcnGraph:
+    """This rank's rows of a destination-partitioned multi-relational graph."""
+
+    def __init__(self, edge_index, range_list, spec, n_rel):
+        ctx = spec.ctx
+        n = spec.n_dst
+        g = RgcnGraph(edge_index, range_list, n, n_rel)
+        self.ctx, self.n_rel, self.n_edges = ctx, int(n_rel), g.n_edges
+        self.n_global, self.b = n, ctx.block(n)
+        r0, r1 = ctx.bounds(n)
+        self.bounds = (r0, r1)
+        self.n_nodes = r1 - r0
+        self.inv_cnt = g.inv_cnt[r0:r1].clone()
+        self.fwd = slice_csr(g.fwd, r0, r1, ctx.world * self.b * n_rel)
+        self.bwd = slice_csr(g.bwd, r0 * n_rel, r1 * n_rel, ctx.world * self.b)
+
+
 class EdgeStruct:
     """Endpoint CSR of an edge list (deterministic DistMult backward w.r.t. z).
 
@@ -283,12 +341,24 @@ def _capturing():
 
 
 def gcn_graph(edge_index, n_src, n_dst, edge_weight=None, improved=False, bipartite=False, want_aug=False):
+    from . import parallel
+    spec = parallel.lookup(edge_index)
+    if spec is not None:          # destination-partitioned edge list: node counts come from the registry
+        key = ("dgcn", _Cache.tkey(edge_index), _Cache.tkey(edge_weight), improved, bipartite, spec.ctx.rank)
+        return _cache.get(key, (edge_index, edge_weight),
+                          lambda: DistGcnGraph(edge_index, spec, edge_weight, improved, bipartite))
     key = ("gcn", _Cache.tkey(edge_index), _Cache.tkey(edge_weight), n_src, n_dst, improved, bipartite, want_aug)
     return _cache.get(key, (edge_index, edge_weight),
                       lambda: GcnGraph(edge_index, n_src, n_dst, edge_weight, improved, bipartite, want_aug))
 
 
 def rgcn_graph(edge_index, range_list, n_nodes, n_rel):
+    from . import parallel
+    spec = parallel.lookup(edge_index)
+    if spec is not None:
+        key = ("drgcn", _Cache.tkey(edge_index), _Cache.tkey(range_list), n_rel, spec.ctx.rank)
+        return _cache.get(key, (edge_index, range_list),
+                          lambda: DistRgcnGraph(edge_index, range_list, spec, n_rel))
     key = ("rgcn", _Cache.tkey(edge_index), _Cache.tkey(range_list), n_nodes, n_rel)
     return _cache.get(key, (edge_index, range_list), lambda: RgcnGraph(edge_index, range_list, n_nodes, n_rel))
 

@@ -241,4 +241,5 @@ class interGraph(Module):
         if not self.if_one_external:
             return h                                                  # layers.py:372-373
         down = getattr(self, "target_feat_down", None)
-        return ops.InterTail.apply(h, self.target_feat, down, "cat" if mod == "cat" else "add")
+        return ops.InterTail.apply(h, self.target_feat, down, "cat" if mod == "cat" else "add",
+                                   getattr(g, "ctx", None))

@@ -46,6 +46,38 @@ def _new(n, f, like):
     return torch.empty((n, f), dtype=torch.float32, device=like.device)
 
 
+class Slot:
+    """Rows of a matrix that may have to be all-gathered before a SpMM reads them.
+
+    Single GPU: a plain ``[n, f]`` matrix (``full`` is the matrix itself).  Partitioned run
+    (``parallel.py``): ``full`` is the ``[world*B, f]`` gather buffer, ``m`` views this rank's slot, so
+    the producing kernel writes in place and ``gather()`` completes the buffer with one in-place
+    NCCL all-gather (gathered row index == global node id)."""
+    __slots__ = ("m", "full", "dctx")
+
+    def __init__(self, n_local, f, like, dctx=None, block=None):
+        self.dctx = dctx
+        if dctx is None:
+            t = _new(n_local, f, like)
+            self.m, self.full = M(t), M(t)
+        else:
+            buf = _new(dctx.world * block, f, like)
+            self.full = M(buf)
+            self.m = M(buf[dctx.rank * block: dctx.rank * block + n_local])
+
+    def gather(self):
+        if self.dctx is not None:
+            self.dctx.all_gather_slots(self.full.t)
+        return self.full
+
+
+def _reduce(dctx, t):
+    """Partial sums of a replicated parameter's gradient -> all-reduce (no-op on one GPU)."""
+    if dctx is not None:
+        dctx.all_reduce_(t)
+    return t
+
+
 # ----------------------------------------------------------------------------
 # thin kernel wrappers
 # ----------------------------------------------------------------------------
@@ -110,6 +142,8 @@ class GcnStack(torch.autograd.Function):
             if w.size(0) != dims[l]:
                 raise RuntimeError(f"layer {l}: weight expects {w.size(0)} input features, got {dims[l]}")
         dev = x0.device
+        dctx = getattr(graph, "ctx", None)
+        b_src = graph.b_src if dctx is not None else None
         outs = []      # M views of H_0 .. H_L
         if catout:
             buf = _new(graph.n_dst, sum(dims), x0)
@@ -123,15 +157,15 @@ class GcnStack(torch.autograd.Function):
         for l in range(n_layers):
             w = weights[l].contiguous()
             k, f = dims[l], dims[l + 1]
-            y = _new(graph.n_src, f, x0)
+            y = Slot(graph.n_src, f, x0, dctx, b_src)
             xin = outs[l]
-            sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.data_ptr(), f, dev)
+            sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, y.m.ld, dev)
             if catout:
                 hl = M(buf, offs[l + 1], f)
             else:
                 hl = M(_new(graph.n_dst, f, x0))
             b = biases[l].contiguous() if biases[l] is not None else None
-            spmm(graph.fwd, M(y), hl, f, bias=b, relu=relu_flags[l])
+            spmm(graph.fwd, y.gather(), hl, f, bias=b, relu=relu_flags[l])
             outs.append(hl)
         ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
         ctx.has_bias = [b is not None for b in biases]
@@ -155,6 +189,8 @@ class GcnStack(torch.autograd.Function):
             outs = [M(a) for a in acts]
         g = _as_rows(grad_out, "grad")
         dev = g.device
+        dctx = getattr(graph, "ctx", None)
+        b_dst = graph.b_dst if dctx is not None else None
         if catout:
             offs = [sum(dims[:i]) for i in range(len(dims))]
             gs = [M(g, offs[i], dims[i]) for i in range(len(dims))]
@@ -163,40 +199,49 @@ class GcnStack(torch.autograd.Function):
             gs = None
             dh = M(g)
         grads = [None] * (2 * n_layers)
-        dz_ready = False          # True when `dh` already carries the ReLU mask of its own layer
+        dz_slot = None            # set when `dh` already is a masked dZ living in a gatherable slot
         dx0 = None
         for l in range(n_layers, 0, -1):
             f, k = dims[l], dims[l - 1]
             h_l, h_prev = outs[l], outs[l - 1]
-            if relu_flags[l - 1] and not dz_ready:
-                dz = M(_new(graph.n_dst, f, g))
-                relu_bwd(dh, h_l, dz)
+            if dz_slot is not None:
+                dz = dz_slot
+            elif relu_flags[l - 1]:
+                dz = Slot(graph.n_dst, f, g, dctx, b_dst)
+                relu_bwd(dh, h_l, dz.m)
+            elif dctx is not None:
+                dz = Slot(graph.n_dst, f, g, dctx, b_dst)
+                map2d(_lib.EW_COPY, dh, dz.m)
             else:
-                dz = dh
+                dz = Slot.__new__(Slot)
+                dz.m, dz.full, dz.dctx = dh, dh, None
             if ctx.has_bias[l - 1] and ctx.needs_input_grad[4 + 2 * (l - 1) + 1]:
                 db = torch.empty(f, dtype=torch.float32, device=dev)
-                colsum(dz, db)
-                grads[2 * (l - 1) + 1] = db
+                colsum(dz.m, db)
+                grads[2 * (l - 1) + 1] = _reduce(dctx, db)
             dy = M(_new(graph.n_src, f, g))
-            spmm(graph.bwd, dz, dy, f)
+            spmm(graph.bwd, dz.gather(), dy, f)
             if ctx.needs_input_grad[4 + 2 * (l - 1)]:
                 dw = torch.empty((k, f), dtype=torch.float32, device=dev)
                 # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
                 sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f, dev)
-                grads[2 * (l - 1)] = dw
+                grads[2 * (l - 1)] = _reduce(dctx, dw)
             need_prev = (l > 1) or ctx.needs_input_grad[0]
+            dz_slot = None
             if need_prev:
                 w = weights[l - 1]
-                dprev = M(_new(graph.n_src, k, g))
                 addend = gs[l - 1] if catout else None
                 mask = h_prev if (l > 1 and relu_flags[l - 2]) else None
-                # dH_{l-1} = dY W^T (+ concat-slice grad) (masked by ReLU of layer l-1)
-                sgemm(False, True, graph.n_src, k, f, dy.ptr, dy.ld, w.data_ptr(), f, dprev.ptr, dprev.ld, dev,
+                # dH_{l-1} = dY W^T (+ concat-slice grad) (masked by ReLU of layer l-1); when it is the
+                # next layer's dZ it is produced straight into that layer's gather slot
+                dprev = Slot(graph.n_src, k, g, dctx if mask is not None else None, b_dst)
+                sgemm(False, True, graph.n_src, k, f, dy.ptr, dy.ld, w.data_ptr(), f, dprev.m.ptr, dprev.m.ld, dev,
                       addend=addend, mask=mask)
-                dh = dprev
-                dz_ready = mask is not None
+                dh = dprev.m
+                if mask is not None:
+                    dz_slot = dprev
                 if l == 1:
-                    dx0 = dprev.t
+                    dx0 = dprev.m.t
         return (dx0, None, None, None) + tuple(grads)
 
 
@@ -218,6 +263,8 @@ class RgcnStack(torch.autograd.Function):
             raise RuntimeError(f"x has {x0.size(0)} rows but the graph has {n} nodes")
         dims = [x0.size(1)] + [rt.size(1) for rt in root]
         dev = x0.device
+        dctx = getattr(graph, "ctx", None)
+        blk = graph.b if dctx is not None else None
         outs, ws_list = [], []
         if catout:
             buf = _new(n, sum(dims), x0)
@@ -239,14 +286,15 @@ class RgcnStack(torch.autograd.Function):
             sgemm(False, False, r, k * f, nb, at.data_ptr(), nb, bs.data_ptr(), k * f, w.data_ptr(), k * f, dev)
             xin = outs[l]
             # Y[:, r, :] = X W[r] for every relation at once (transform-then-gather)
-            y = torch.empty((n, r, f), dtype=torch.float32, device=dev)
-            sgemm(False, False, n, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.data_ptr(), r * f, dev,
+            y = Slot(n, r * f, x0, dctx, blk)
+            sgemm(False, False, n, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, r * f, dev,
                   batch=r, sa=0, sb=k * f, sc=f)
             hl = M(buf, offs[l + 1], f) if catout else M(_new(n, f, x0))
             # root term first, then the segmented mean accumulates onto it (layers.py:193)
             sgemm(False, False, n, f, k, xin.ptr, xin.ld, rt.data_ptr(), f, hl.ptr, hl.ld, dev)
             b = bias[l].contiguous() if bias[l] is not None else None
-            spmm(graph.fwd, M(y.view(n * r, f)), hl, f, row_scale=graph.inv_cnt, bias=b, addend=hl,
+            yfull = y.gather().t
+            spmm(graph.fwd, M(yfull.view(yfull.size(0) * r, f)), hl, f, row_scale=graph.inv_cnt, bias=b, addend=hl,
                  relu=relu_flags[l])
             outs.append(hl)
             ws_list.append((w, bs, at, rt))
@@ -273,6 +321,8 @@ class RgcnStack(torch.autograd.Function):
             outs = [M(a) for a in acts]
         g = _as_rows(grad_out, "grad")
         dev = g.device
+        dctx = getattr(graph, "ctx", None)
+        blk = graph.b if dctx is not None else None
         if catout:
             offs = [sum(dims[:i]) for i in range(len(dims))]
             gs = [M(g, offs[i], dims[i]) for i in range(len(dims))]
@@ -281,30 +331,37 @@ class RgcnStack(torch.autograd.Function):
             gs = None
             dh = M(g)
         grads = [None] * (4 * n_layers)
-        dz_ready = False
+        dz_slot = None
         dx0 = None
         for l in range(n_layers, 0, -1):
             f, k = dims[l], dims[l - 1]
             w, bs, at, rt = ws_list[l - 1]
             nb = bs.size(0)
             h_l, h_prev = outs[l], outs[l - 1]
-            if relu_flags[l - 1] and not dz_ready:
-                dz = M(_new(n, f, g))
-                relu_bwd(dh, h_l, dz)
+            if dz_slot is not None:
+                dzs = dz_slot
+            elif relu_flags[l - 1]:
+                dzs = Slot(n, f, g, dctx, blk)
+                relu_bwd(dh, h_l, dzs.m)
+            elif dctx is not None:
+                dzs = Slot(n, f, g, dctx, blk)
+                map2d(_lib.EW_COPY, dh, dzs.m)
             else:
-                dz = dh
+                dzs = Slot.__new__(Slot)
+                dzs.m, dzs.full, dzs.dctx = dh, dh, None
+            dz = dzs.m
             base = 4 + 4 * (l - 1)
             if ctx.has_bias[l - 1] and ctx.needs_input_grad[base + 3]:
                 db = torch.empty(f, dtype=torch.float32, device=dev)
                 colsum(dz, db)
-                grads[4 * (l - 1) + 3] = db
+                grads[4 * (l - 1) + 3] = _reduce(dctx, db)
             # dY[(j,r)] = sum_{e: src=j, rel=r} dZ[dst_e] / c_dst   (transpose CSR, atomic-free)
             dy = torch.empty((n * r, f), dtype=torch.float32, device=dev)
-            spmm(graph.bwd, dz, M(dy), f)
+            spmm(graph.bwd, dzs.gather(), M(dy), f)
             if ctx.needs_input_grad[base + 2]:
                 droot = torch.empty((k, f), dtype=torch.float32, device=dev)
                 sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev)
-                grads[4 * (l - 1) + 2] = droot
+                grads[4 * (l - 1) + 2] = _reduce(dctx, droot)
             if ctx.needs_input_grad[base] or ctx.needs_input_grad[base + 1]:
                 # dW[r] = H_{l-1}^T dY[:, r, :]
                 dw = torch.empty((r, k, f), dtype=torch.float32, device=dev)
@@ -314,23 +371,26 @@ class RgcnStack(torch.autograd.Function):
                     datt = torch.empty((r, nb), dtype=torch.float32, device=dev)
                     sgemm(False, True, r, nb, k * f, dw.data_ptr(), k * f, bs.data_ptr(), k * f, datt.data_ptr(), nb,
                           dev)
-                    grads[4 * (l - 1) + 1] = datt
+                    grads[4 * (l - 1) + 1] = _reduce(dctx, datt)
                 if ctx.needs_input_grad[base]:
                     dbasis = torch.empty((nb, k, f), dtype=torch.float32, device=dev)
                     sgemm(True, False, nb, k * f, r, at.data_ptr(), nb, dw.data_ptr(), k * f, dbasis.data_ptr(),
                           k * f, dev)
-                    grads[4 * (l - 1)] = dbasis
+                    grads[4 * (l - 1)] = _reduce(dctx, dbasis)
             need_prev = (l > 1) or ctx.needs_input_grad[0]
+            dz_slot = None
             if need_prev:
-                dprev = M(_new(n, k, g))
                 addend = gs[l - 1] if catout else None
                 mask = h_prev if (l > 1 and relu_flags[l - 2]) else None
+                dps = Slot(n, k, g, dctx if mask is not None else None, blk)
+                dprev = dps.m
                 # dH_{l-1} = dZ root^T (+ concat grad), then += sum_r dY[:, r, :] W[r]^T, then ReLU mask
                 sgemm(False, True, n, k, f, dz.ptr, dz.ld, rt.data_ptr(), f, dprev.ptr, dprev.ld, dev, addend=addend)
                 sgemm(False, True, n, k, f, dy.data_ptr(), r * f, w.data_ptr(), f, dprev.ptr, dprev.ld, dev,
                       batch=r, sa=f, sb=k * f, sc=0, batch_reduce=True, accumulate=True, mask=mask)
                 dh = dprev
-                dz_ready = mask is not None
+                if mask is not None:
+                    dz_slot = dps
                 if l == 1:
                     dx0 = dprev.t
         return (dx0, None, None, None) + tuple(grads)
@@ -352,7 +412,8 @@ def abs_bwd(g, t, dst, scale):
 
 class InterTail(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, target_feat, target_feat_down, mod):
+    def forward(ctx, h, target_feat, target_feat_down, mod, dctx=None):
+        ctx.dctx = dctx
         h = _as_rows(h, "h")
         t = _as_rows(target_feat, "target_feat")
         n, f, ft = h.size(0), h.size(1), t.size(1)
@@ -391,14 +452,14 @@ class InterTail(torch.autograd.Function):
             (t,) = ctx.saved_tensors
             dt = _new(n, ft, g)
             abs_bwd(M(g, f, ft), M(t), M(dt), 1.0)
-            return g[:, :f], dt, None, None
+            return g[:, :f], dt, None, None, None
         dh = _new(n, f, g)
         axpby(M(g), 0.5, None, 0.0, M(dh))
         if ctx.kind == 1:
             (t,) = ctx.saved_tensors
             dt = _new(n, ft, g)
             abs_bwd(M(g), M(t), M(dt), 0.5)
-            return dh, dt, None, None
+            return dh, dt, None, None, None
         t, d, u = ctx.saved_tensors
         du = _new(n, f, g)
         relu_bwd(M(dh), M(u), M(du))                      # 0.5 * g where t D > 0
@@ -406,7 +467,7 @@ class InterTail(torch.autograd.Function):
         sgemm(False, True, n, ft, f, du.data_ptr(), f, d.data_ptr(), d.stride(0), dt.data_ptr(), ft, dev)
         dd = torch.empty((ft, f), dtype=torch.float32, device=dev)
         sgemm(True, False, ft, f, n, t.data_ptr(), t.stride(0), du.data_ptr(), f, dd.data_ptr(), f, dev)
-        return dh, dt, dd, None
+        return dh, dt, _reduce(ctx.dctx, dd), None, None
 
 
 # ----------------------------------------------------------------------------

@@ -10,6 +10,7 @@ Used by ``bench.py``, ``__graft_entry__.smoke()`` and the parity tests.
 import torch
 from torch.nn import Module, Parameter
 
+from . import parallel
 from .decoder import multiClassInnerProductDecoder, multiRelaInnerProductDecoder
 from .layers import homoGraph, interGraph
 from .losses import link_prediction_loss, node_classification_loss
@@ -31,12 +32,24 @@ class PoseModel(Module):
                        range_list=data["dd_range_list"], if_catout=True)
 
     def forward(self, data, neg_edge_index=None):
-        """Returns (loss, z, pos_score, neg_score) for one training step's forward."""
+        """Returns (loss, z, pos_score, neg_score) for one training step's forward.
+
+        Partitioned run (``data`` from ``shard_pose``): ``z`` holds this rank's drug rows, the scores
+        are those of this rank's slice of the edge lists, the loss is the global mean."""
         z = self.embed(data)
-        neg = data["neg_edge_index"] if neg_edge_index is None else neg_edge_index
-        pos_score = self.dmt(z, data["dd_edge_index"], data["dd_edge_type"])
-        neg_score = self.dmt(z, neg, data["dd_edge_type"])
-        return link_prediction_loss(pos_score, neg_score), z, pos_score, neg_score
+        dctx = data.get("dist")
+        if dctx is None:
+            neg = data["neg_edge_index"] if neg_edge_index is None else neg_edge_index
+            pos_score = self.dmt(z, data["dd_edge_index"], data["dd_edge_type"])
+            neg_score = self.dmt(z, neg, data["dd_edge_type"])
+            return link_prediction_loss(pos_score, neg_score), z, pos_score, neg_score
+        neg = data["neg_edge_index_local"] if neg_edge_index is None else neg_edge_index
+        z_full = parallel.all_gather_rows(z, dctx, data["n_d_global"])
+        pos_score = self.dmt(z_full, data["dd_edge_index_local"], data["dd_edge_type_local"])
+        neg_score = self.dmt(z_full, neg, data["dd_edge_type_local"])
+        loss = parallel.global_mean_loss(link_prediction_loss(pos_score, neg_score), pos_score.numel(),
+                                         data["e_dd_global"], dctx)
+        return loss, z, pos_score, neg_score
 
 
 class AminerModel(Module):
@@ -75,6 +88,93 @@ class FreebaseDModel(Module):
         z = self.aa((z + z1 + self.aa_embeddings) / 3, data["aa_edge_index"])       # freebase-d.py:160-164
         score = self.mcip(z, data["train_node_idx"])
         return node_classification_loss(score, data["train_node_class"]), z, score
+
+
+class ChainModel(Module):
+    """Three-supervertex chain A -> B -> C for node classification on C (BASELINE config 5: the
+    aminer wiring, ``GripNet-aminer.py:103-108``, extended by one more supervertex).  Widths default
+    to the F=64 hidden size of SURVEY.md §8d."""
+
+    def __init__(self, n_a, n_b, n_c, n_class, hid=64, out=32):
+        super().__init__()
+        self.aa = homoGraph([hid, hid, hid], start_graph=True, in_dim=n_a)                    # -> 3*hid
+        self.ab = interGraph(3 * hid, hid, n_b, target_feat_dim=hid)                          # -> 2*hid
+        self.bb = homoGraph([2 * hid, hid, hid])                                              # -> 4*hid
+        self.bc = interGraph(4 * hid, hid, n_c, target_feat_dim=hid)                          # -> 2*hid
+        self.cc = homoGraph([2 * hid, hid, out])                                              # -> 3*hid + out
+        self.mcip = multiClassInnerProductDecoder(3 * hid + out, n_class)
+
+    def forward(self, data):
+        z = self.aa(None, data["aa_edge_index"], if_catout=True)
+        z = self.ab(z, data["ab_edge_index"], if_relu=True, mod="cat")
+        z = self.bb(z, data["bb_edge_index"], if_catout=True)
+        z = self.bc(z, data["bc_edge_index"], if_relu=True, mod="cat")
+        z = self.cc(z, data["cc_edge_index"], if_catout=True)
+        score = self.mcip(z, data["train_node_idx"])          # local ids of this rank's labelled nodes
+        loss = node_classification_loss(score, data["train_node_class"])
+        dctx = data.get("dist")
+        if dctx is not None:
+            loss = parallel.global_mean_loss(loss, score.size(0), data["n_train_global"], dctx)
+        return loss, z, score
+
+
+def chain_edges_per_epoch(g):
+    """Input edges traversed by one forward of ``ChainModel`` (2 GCN layers per supervertex)."""
+    return (2 * g["aa_edge_index"].shape[1] + g["ab_edge_index"].shape[1] + 2 * g["bb_edge_index"].shape[1]
+            + g["bc_edge_index"].shape[1] + 2 * g["cc_edge_index"].shape[1])
+
+
+# ----------------------------------------------------------------------------------------------
+# destination-partitioned runs (parallel.py): every rank holds the GLOBAL edge lists (registered as
+# partitioned), its own rows of the row-partitioned parameters and its slice of the decoder lists
+# ----------------------------------------------------------------------------------------------
+def shard_pose(g, dctx, device):
+    """Per-rank ``data`` dict for ``PoseModel`` built with LOCAL node counts."""
+    d = to_device(g, device)
+    n_g, n_d = g["n_g"], g["n_d"]
+    parallel.distribute_edges(d["gg_edge_index"], dctx, n_g)
+    parallel.distribute_edges(d["gd_edge_index"], dctx, n_g, n_d)
+    parallel.distribute_edges(d["dd_edge_index"], dctx, n_d)
+    e = g["dd_edge_index"].shape[1]
+    e0, e1 = dctx.edge_slice(e)
+    d.update({
+        "dist": dctx, "n_g_global": n_g, "n_d_global": n_d, "e_dd_global": e,
+        "n_g": dctx.local_count(n_g), "n_d": dctx.local_count(n_d), "edge_slice": (e0, e1),
+        "dd_edge_index_local": d["dd_edge_index"][:, e0:e1].contiguous(),
+        "dd_edge_type_local": d["dd_edge_type"][e0:e1].contiguous(),
+        "neg_edge_index_local": d["neg_edge_index"][:, e0:e1].contiguous(),
+    })
+    return d
+
+
+def shard_pose_params(flat, g, dctx):
+    """Rows of the row-partitioned parameters owned by this rank; everything else is replicated."""
+    out = dict(flat)
+    out["gg.embedding"] = dctx.shard_rows(flat["gg.embedding"], g["n_g"]).clone()
+    out["gd.target_feat"] = dctx.shard_rows(flat["gd.target_feat"], g["n_d"]).clone()
+    return out
+
+
+ROW_PARTITIONED = {"gg.embedding": "n_g", "gd.target_feat": "n_d",
+                   "aa.embedding": "n_a", "ab.target_feat": "n_b", "bc.target_feat": "n_c"}
+
+
+def shard_chain(g, dctx, device):
+    """Per-rank ``data`` dict for ``ChainModel`` (labelled nodes of C are handled by their owner rank)."""
+    d = to_device(g, device)
+    n_a, n_b, n_c = g["n_a"], g["n_b"], g["n_c"]
+    parallel.distribute_edges(d["aa_edge_index"], dctx, n_a)
+    parallel.distribute_edges(d["ab_edge_index"], dctx, n_a, n_b)
+    parallel.distribute_edges(d["bb_edge_index"], dctx, n_b)
+    parallel.distribute_edges(d["bc_edge_index"], dctx, n_b, n_c)
+    parallel.distribute_edges(d["cc_edge_index"], dctx, n_c)
+    r0, r1 = dctx.bounds(n_c)
+    idx, cls = d["train_node_idx"], d["train_node_class"]
+    mine = ((idx >= r0) & (idx < r1)).nonzero().view(-1)
+    d.update({"dist": dctx, "n_train_global": int(idx.numel()),
+              "n_a": dctx.local_count(n_a), "n_b": dctx.local_count(n_b), "n_c": r1 - r0,
+              "train_node_idx": (idx[mine] - r0).contiguous(), "train_node_class": cls[mine].contiguous()})
+    return d
 
 
 def to_device(data, device):

@@ -86,6 +86,83 @@ def nc_graph(n_p, e_pp, n_a, e_pa, e_aa, n_class=8, train_frac=0.2, seed=1111, n
     return g
 
 
+def pose_graph_scaled(scale, seed=1111):
+    """pose-0-shaped supergraph with ``scale`` times the nodes and edges (weak scaling over ``scale``
+    GPUs: per-GPU work stays that of pose-0).  ``scale == 1`` is exactly ``pose_graph()``."""
+    if scale == 1:
+        return pose_graph(seed=seed)
+    return pose_graph(n_g=19081 * scale, gg_pairs=715612 * scale, n_d=645 * scale, e_gd=18596 * scale, n_rel=16,
+                      dd_pairs_per_rel=12500 * scale, seed=seed)
+
+
+# ---------------------------------------------------------------------------
+# config 5: scaled three-supervertex chain with power-law (R-MAT) degrees, generated on the device
+# ---------------------------------------------------------------------------
+def rmat_edges(log2_n, n_edges, device, gen, probs=(0.57, 0.19, 0.19, 0.05), n_nodes=None, chunk=1 << 26):
+    """R-MAT edge list over ``2**log2_n`` ids (recursive quadrant choice with probabilities a,b,c,d),
+    ids then scattered by a fixed multiplicative hash so hubs do not cluster in one partition block.
+    Returns int64 ``[2, n_edges]`` on ``device``; ids are folded into ``[0, n_nodes)``."""
+    a, b, c, _ = probs
+    n = 1 << log2_n
+    n_nodes = n if n_nodes is None else n_nodes
+    out = torch.empty((2, n_edges), dtype=torch.int64, device=device)
+    for s in range(0, n_edges, chunk):
+        m = min(chunk, n_edges - s)
+        src = torch.zeros(m, dtype=torch.int64, device=device)
+        dst = torch.zeros(m, dtype=torch.int64, device=device)
+        for _ in range(log2_n):
+            r = torch.rand(m, device=device, generator=gen)
+            src = src * 2 + (r >= a + b).to(torch.int64)                 # quadrants c, d -> lower half (src bit 1)
+            dst = dst * 2 + (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)   # b, d -> dst bit 1
+        # scatter ids: odd multiplier mod 2^k is a bijection
+        src = (src * 0x9E3779B1 + 0x7F4A7C15) & (n - 1)
+        dst = (dst * 0x85EBCA6B + 0x2545F491) & (n - 1)
+        out[0, s:s + m] = src % n_nodes
+        out[1, s:s + m] = dst % n_nodes
+    return out
+
+
+def chain_graph(n_a, n_b, n_c, e_aa, e_ab, e_bb, e_bc, e_cc, device, n_class=8, train_frac=0.2, seed=1111):
+    """Config 5: supervertex chain A -> B -> C, intra graphs R-MAT and mirrored
+    (undirected), inter graphs R-MAT sources x uniform targets; labels on ``train_frac`` of C."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+
+    def log2_ceil(n):
+        k = 1
+        while (1 << k) < n:
+            k += 1
+        return k
+
+    def homo(n, e):
+        half = rmat_edges(log2_ceil(n), e // 2, device, gen, n_nodes=n)
+        return torch.cat([half, half.flip(0)], dim=1)
+
+    def bip(ns, nt, e):
+        src = rmat_edges(log2_ceil(ns), e, device, gen, n_nodes=ns)[0]
+        dst = torch.randint(0, nt, (e,), device=device, generator=gen)
+        return torch.stack([src, dst])
+
+    g = {"n_a": n_a, "n_b": n_b, "n_c": n_c, "n_class": n_class,
+         "aa_edge_index": homo(n_a, e_aa), "ab_edge_index": bip(n_a, n_b, e_ab),
+         "bb_edge_index": homo(n_b, e_bb), "bc_edge_index": bip(n_b, n_c, e_bc),
+         "cc_edge_index": homo(n_c, e_cc)}
+    n_train = max(1, int(n_c * train_frac))
+    g["train_node_idx"] = torch.randperm(n_c, device=device, generator=gen)[:n_train].sort().values
+    g["train_node_class"] = torch.randint(0, n_class, (n_train,), device=device, generator=gen)
+    return g
+
+
+def chain_full(device, seed=1111):
+    """~10 M nodes, ~520 M directed edges."""
+    return chain_graph(4_000_000, 4_000_000, 2_000_000, 200_000_000, 50_000_000, 200_000_000, 50_000_000,
+                       20_000_000, device, seed=seed)
+
+
+def chain_small(device, seed=1111):
+    return chain_graph(3000, 2500, 1500, 40_000, 9_000, 30_000, 8_000, 12_000, device, n_class=5, seed=seed)
+
+
 # presets -------------------------------------------------------------------
 def pose_small(seed=1111, weighted=False):
     return pose_graph(n_g=300, gg_pairs=1500, n_d=40, e_gd=200, n_rel=5, dd_pairs_per_rel=60,

@@ -77,6 +77,11 @@ int gn_csr_from_keys(const int32_t* keys, int64_t n, int32_t n_rows,
                      int32_t* rowptr /*[n_rows+1]*/, int32_t* perm /*[n]*/,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* out[i] = rowptr[r0+i] - rowptr[r0], i in [0, n_rows]: rows [r0, r0+n_rows) of a CSR as a
+ * stand-alone CSR — the per-rank slice of a destination-partitioned graph (new design: the
+ * reference has no multi-GPU path). */
+int gn_rowptr_slice(const int32_t* rowptr, int32_t r0, int32_t n_rows, int32_t* out, void* stream);
+
 /* Row-split work list for a CSR: a row of length L gets max(1, ceil(L/chunk_len))
  * chunks.  n_chunks_out (device int32) receives the total. */
 size_t gn_build_chunks_workspace_bytes(int32_t n_rows);

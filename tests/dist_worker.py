@@ -1,0 +1,137 @@
+"""Multi-rank parity worker for the destination-partitioned path (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
+        tests/dist_worker.py
+
+Every rank (1) runs the partitioned PoseModel / ChainModel on its block of rows, (2) runs the SAME global
+model on its own GPU through the single-GPU path, and checks that the partitioned outputs / gradients are
+the row slices (row-partitioned tensors) or equal (replicated parameters, loss) of the global ones within
+1e-5 relative; the pose case is also checked against the CPU oracle on rank 0.  With WORLD_SIZE unset it
+runs as a single rank (degenerate partition).
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+TOL = 1e-5
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if a.shape != b.shape:
+        return float("inf")
+    if b.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def check(name, a, b, tol=TOL):
+    e = rel(a, b)
+    assert e < tol, f"{name}: rel err {e:.3e}"
+    return e
+
+
+def run_pose(dctx, dev, with_oracle):
+    from gripnet_b200 import graph as G
+    from gripnet_b200.pipelines import PoseModel, load_flat_params, shard_pose, shard_pose_params, to_device
+    from oracle import synth
+    g = synth.pose_medium()
+    p = synth.pose_params(g)
+    # ---- global model, single-GPU path
+    ref = load_flat_params(PoseModel(g["n_g"], g["n_d"], g["n_rel"]), p).to(dev)
+    loss_g, z_g, pos_g, neg_g = ref(to_device(g, dev))
+    loss_g.backward()
+    # ---- partitioned model
+    G.clear_cache()
+    data = shard_pose(g, dctx, dev)
+    m = load_flat_params(PoseModel(data["n_g"], data["n_d"], g["n_rel"]), shard_pose_params(p, g, dctx)).to(dev)
+    m.dmt.dist_ctx = dctx
+    loss, z, pos, neg = m(data)
+    loss.backward()
+    worst = 0.0
+    r0, r1 = dctx.bounds(g["n_d"])
+    e0, e1 = data["edge_slice"]
+    worst = max(worst, check("z", z, z_g[r0:r1]), check("loss", loss, loss_g),
+                check("pos", pos, pos_g[e0:e1]), check("neg", neg, neg_g[e0:e1]))
+    named_g = dict(ref.named_parameters())
+    for k, v in m.named_parameters():
+        gg = named_g[k].grad
+        if gg is None:
+            assert v.grad is None, k
+            continue
+        if k == "gg.embedding":
+            gg = dctx.shard_rows(gg, g["n_g"])
+        elif k == "gd.target_feat":
+            gg = dctx.shard_rows(gg, g["n_d"])
+        worst = max(worst, check("grad." + k, v.grad, gg, 2e-5))
+    if with_oracle:
+        from oracle import port
+        pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        loss_o, z_o, _, _ = port.pose_forward(pl, g)
+        worst = max(worst, check("z vs oracle", z, z_o[r0:r1]), check("loss vs oracle", loss, loss_o))
+    return worst
+
+
+def run_chain(dctx, dev):
+    from gripnet_b200 import graph as G
+    from gripnet_b200.pipelines import ROW_PARTITIONED, ChainModel, shard_chain
+    from gripnet_b200.synthetic import chain_small
+    g = chain_small(dev)
+    torch.manual_seed(5)
+    ref = ChainModel(g["n_a"], g["n_b"], g["n_c"], g["n_class"], hid=16, out=8).to(dev)
+    loss_g, z_g, _ = ref(g)
+    loss_g.backward()
+    G.clear_cache()
+    data = shard_chain(g, dctx, dev)
+    m = ChainModel(data["n_a"], data["n_b"], data["n_c"], g["n_class"], hid=16, out=8).to(dev)
+    m.mcip.dist_ctx = dctx
+    sd = {}
+    for k, v in ref.state_dict().items():
+        sd[k] = dctx.shard_rows(v, g[ROW_PARTITIONED[k]]).clone() if k in ROW_PARTITIONED else v.clone()
+    m.load_state_dict(sd)
+    loss, z, _ = m(data)
+    loss.backward()
+    r0, r1 = dctx.bounds(g["n_c"])
+    worst = max(check("chain z", z, z_g[r0:r1]), check("chain loss", loss, loss_g))
+    named_g = dict(ref.named_parameters())
+    for k, v in m.named_parameters():
+        gg = named_g[k].grad
+        if gg is None:
+            assert v.grad is None, k
+            continue
+        if k in ROW_PARTITIONED:
+            gg = dctx.shard_rows(gg, g[ROW_PARTITIONED[k]])
+        worst = max(worst, check("chain grad." + k, v.grad, gg, 2e-5))
+    return worst
+
+
+def main():
+    import gripnet_b200  # noqa: F401
+    from gripnet_b200.parallel import DistContext
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        if "MASTER_ADDR" not in os.environ:
+            os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", "29549"
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    dctx = DistContext()
+    w1 = run_pose(dctx, dev, with_oracle=(rank == 0))
+    w2 = run_chain(dctx, dev)
+    t = torch.tensor([w1, w2], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(f"dist_worker: world={world} OK  worst rel err pose {float(t[0]):.2e}  chain {float(t[1]):.2e}", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
