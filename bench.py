@@ -224,6 +224,7 @@ def build_pose(args, world, rank, dev, dctx):
     return dict(model=model, fwd=fwd, dynamic=[neg_static], edges=e_epoch, h2d=h2d, d2h=d2h, host_loss=host_loss,
                 h2d_bytes=int(neg_static.numel() * 8), d2h_bytes=int(4 + 2 * e_loc * 4), desc=desc,
                 spmm_graph=lambda: model.gg.conv_list[0]._graph, spmm_f=16,
+                row_partitioned=("gg.embedding", "gd.target_feat") if world > 1 else (),
                 e2e_note="negatives from pinned host memory each step; loss and pos/neg scores read back")
 
 
@@ -267,6 +268,7 @@ def build_chain(args, world, rank, dev, dctx):
     return dict(model=model, fwd=fwd, dynamic=[], edges=e_epoch, h2d=h2d, d2h=d2h, host_loss=host_loss,
                 h2d_bytes=int(n_lab * 8), d2h_bytes=int(4 + n_lab * n_class * 4), desc=desc,
                 spmm_graph=lambda: model.aa.conv_list[0]._graph, spmm_f=64,
+                row_partitioned=("aa.embedding", "ab.target_feat", "bc.target_feat") if dctx is not None else (),
                 e2e_note="labels from pinned host memory each step; loss and class scores read back")
 
 
@@ -295,17 +297,23 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from gripnet_b200.parallel import DistContext
-        dctx = DistContext()
+        dctx = DistContext(defer_grad_reduce=True)       # one bucketed all-reduce of weight grads per step
 
     w = (build_pose if args.workload == "pose" else build_chain)(args, world, rank, dev, dctx)
     model, e_epoch = w["model"], w["edges"]
+    replicated = [v for k, v in model.named_parameters() if k not in w.get("row_partitioned", ())]
+
+    def post_backward():
+        if dctx is not None:
+            dctx.reduce_gradients(replicated)
 
     # ---- execution: whole step replayed from one CUDA graph (NCCL collectives included when N > 1)
     execution = "whole step replayed from one CUDA graph"
     step = None
     if not args.eager:
         try:
-            step = CapturedStep(w["fwd"], model.parameters(), dynamic_inputs=w["dynamic"], warmup=max(args.warmup, 3))
+            step = CapturedStep(w["fwd"], model.parameters(), dynamic_inputs=w["dynamic"], warmup=max(args.warmup, 3),
+                                post_backward=post_backward)
         except Exception as e:  # pragma: no cover - capture of NCCL can be refused by the runtime
             if world == 1:
                 raise
@@ -326,6 +334,7 @@ def run_cuda(args):
                 before = gb.launch_count()
                 self.outputs = w["fwd"]()
                 self.outputs[0].backward()
+                post_backward()
                 self.launches_per_replay = gb.launch_count() - before
                 return self.outputs
         step = _Eager()
@@ -428,7 +437,12 @@ def run_cuda(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL teardown with captured graphs alive can block forever: drain, rendezvous, leave
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

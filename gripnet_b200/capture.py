@@ -23,8 +23,9 @@ class CapturedStep:
     ``outputs`` and the parameters' ``.grad``.
     """
 
-    def __init__(self, fn, parameters, dynamic_inputs=(), warmup=3):
+    def __init__(self, fn, parameters, dynamic_inputs=(), warmup=3, post_backward=None):
         self.params = [p for p in parameters]
+        post = post_backward if post_backward is not None else (lambda: None)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -33,6 +34,7 @@ class CapturedStep:
                 self._drop_grads()
                 out = fn()
                 out[0].backward()
+                post()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         for t in dynamic_inputs:
@@ -43,6 +45,7 @@ class CapturedStep:
         with torch.cuda.graph(self.graph):
             self.outputs = fn()
             self.outputs[0].backward()
+            post()                                     # e.g. the bucketed gradient all-reduce of a partitioned run
         self.launches_per_replay = _lib.launch_count() - before
         torch.cuda.synchronize()
 

@@ -74,7 +74,7 @@ class Slot:
 def _reduce(dctx, t):
     """Partial sums of a replicated parameter's gradient -> all-reduce (no-op on one GPU)."""
     if dctx is not None:
-        dctx.all_reduce_(t)
+        dctx.reduce_param_grad_(t)
     return t
 
 

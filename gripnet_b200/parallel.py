@@ -26,12 +26,17 @@ import torch.distributed as dist
 class DistContext:
     """Rank / world / process group of the partitioned run."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, defer_grad_reduce=False):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        # False: every replicated-parameter gradient is all-reduced where it is produced (simple, always
+        # correct).  True: the layer stacks leave partial sums in ``.grad`` and the caller runs ONE bucketed
+        # all-reduce after ``backward()`` with ``reduce_gradients`` (fewer, larger collectives).
+        self.defer_grad_reduce = bool(defer_grad_reduce)
+        self._bucket = None
 
     # ---- block partition -------------------------------------------------
     def block(self, n):
@@ -68,6 +73,27 @@ class DistContext:
         if self.world > 1 and t is not None:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def reduce_param_grad_(self, t):
+        """Gradient of a replicated parameter (a partial sum on every rank)."""
+        if not self.defer_grad_reduce:
+            self.all_reduce_(t)
+        return t
+
+    def reduce_gradients(self, params):
+        """Bucketed all-reduce of the ``.grad`` of replicated parameters (``defer_grad_reduce=True``):
+        pack -> one all-reduce -> unpack.  ``params`` must not contain row-partitioned parameters."""
+        if self.world == 1:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        if not grads:
+            return
+        sizes = [g.numel() for g in grads]
+        if self._bucket is None or self._bucket.numel() != sum(sizes) or self._bucket.device != grads[0].device:
+            self._bucket = torch.empty(sum(sizes), dtype=grads[0].dtype, device=grads[0].device)
+        torch.cat([g.reshape(-1) for g in grads], out=self._bucket)
+        dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM, group=self.group)
+        torch._foreach_copy_([g.view(-1) for g in grads], list(self._bucket.split(sizes)))
 
     def reduce_scatter_rows(self, full):
         """Sum ``full`` ``[world*B, F]`` over ranks and return this rank's ``[B, F]`` block."""
@@ -163,6 +189,8 @@ class _ReplicatedParam(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.dctx.defer_grad_reduce:
+            return g, None
         g = g.contiguous().clone()
         ctx.dctx.all_reduce_(g)
         return g, None
