@@ -24,6 +24,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's own version / INFO lines go to a file instead
+if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+    os.environ["NCCL_DEBUG_FILE"] = "/tmp/nccl_debug_%h_%p.log"
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

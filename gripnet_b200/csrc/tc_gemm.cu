@@ -1,0 +1,413 @@
+// K2/K6 tensor path: C[M,N] = A[M,K] * op(B) on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM) with fp32-grade accuracy by an
+// error-compensated 3xTF32 split.
+//
+// Why: north_star item 3 sends the dense X.W / X.W_r feature transforms to tcgen05, but
+// the parity bar is 1e-5 relative in fp32 and a TF32 operand keeps 10 mantissa bits.
+// Every operand element is split  x = hi + lo  (hi = rna-tf32(x), lo = rna-tf32(x - hi))
+// while it is staged, and each k-step issues three MMAs into the same fp32 accumulator:
+// lo*hi + hi*lo + hi*hi (the lo*lo term, <= 2^-22 relative, is dropped).
+//
+// Shape regime: M = number of nodes (huge), K <= 512, N <= 512 (feature widths).  These
+// products are HBM-bound (read A once, write C once), so the kernel is built around the
+// A stream, not around the tensor pipe:
+//   * one CTA per 128-row tile of A (x one N tile of <= 256 columns); 10 warps:
+//       warps 0-7  stage A: coalesced 128-bit global loads -> split -> st.shared in the
+//                  canonical no-swizzle K-major core-matrix layout (software-pipelined
+//                  one k-block ahead), later the epilogue (tcgen05.ld -> fused addend /
+//                  ReLU mask -> 128-bit stores);
+//       warp 8     allocates TMEM and issues the MMAs (one lane), commits to mbarriers;
+//       warp 9     brings the pre-split image of B for each k-block with ONE bulk
+//                  async copy (cp.async.bulk, TMA engine) completing on the stage's mbarrier;
+//   * B is tiny and shared by every CTA: a prep kernel writes its hi/lo split once per call,
+//     already in the shared-memory layout (k-block major), into the caller's workspace;
+//   * 2-3 smem stages, full/empty mbarriers; tcgen05.commit releases a stage when the
+//     MMAs that read it have retired.
+#include "common.cuh"
+
+namespace gn {
+namespace tc {
+
+constexpr int BM = 128;          // rows per CTA tile == UMMA M
+constexpr int BK = 32;           // floats per k-block (4 UMMA k-steps of 8)
+constexpr int CHUNKS = BK / 4;   // 16-byte k-chunks per k-block
+constexpr int kLoaderWarps = 8;
+constexpr int kLoaderThreads = kLoaderWarps * 32;
+constexpr int kThreads = (kLoaderWarps + 2) * 32;
+constexpr int kMaxNt = 256;
+
+// one "plane" = all rows of one 16-byte k-chunk, 16 B per row, plus 16 B of padding so that
+// the 8 chunks of one row land in 8 different 16-byte bank groups (conflict-free staging)
+__host__ __device__ constexpr int plane_bytes(int rows) { return rows * 16 + 16; }
+__host__ __device__ constexpr int part_bytes(int rows) { return CHUNKS * plane_bytes(rows); }
+__host__ __device__ constexpr int stage_bytes(int nt) { return 2 * part_bytes(BM) + 2 * part_bytes(nt); }
+
+struct Params {
+  int M, N, K;
+  const float* A; int64_t lda;
+  float* C; int64_t ldc;
+  const float* addend; int64_t ldd;
+  const float* mask; int64_t ldm;
+  const char* b_image;   // [n_tile][k_block][hi|lo][chunk][row][4 floats] (+ plane padding)
+  int nt;                // columns per N tile (multiple of 16, <= 256)
+  int n_kb;              // k-blocks
+  int stages;
+  int tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+  lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+}
+
+// ---- mbarrier / proxy / tcgen05 wrappers (PTX ISA 8.6+, sm_100a) ------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B stored
+// contiguously (128 B); SBO = distance between 8-row groups, LBO = distance between the two
+// 16-byte k-chunks of one UMMA k-step.  Blackwell descriptor version = 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  return d;
+}
+
+// instruction descriptor for kind::tf32: D = F32, A = B = TF32, both K-major
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// B image: hi/lo split of op(B), laid out exactly as one smem stage wants it
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) b_image_kernel(const float* __restrict__ B, int64_t ldb, int transB, int K, int N,
+                                                      int nt, int n_kb, char* __restrict__ image) {
+  // one thread per (n_tile, k_block, chunk, row)
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int n_tiles = (N + nt - 1) / nt;
+  const int64_t total = int64_t(n_tiles) * n_kb * CHUNKS * nt;
+  if (idx >= total) return;
+  const int row = int(idx % nt);
+  const int c = int((idx / nt) % CHUNKS);
+  const int kb = int((idx / (int64_t(nt) * CHUNKS)) % n_kb);
+  const int t = int(idx / (int64_t(nt) * CHUNKS * n_kb));
+  const int n = t * nt + row;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int k = kb * BK + c * 4 + e;
+    float x = 0.f;
+    if (n < N && k < K) x = transB ? __ldg(B + int64_t(n) * ldb + k) : __ldg(B + int64_t(k) * ldb + n);
+    v[e] = x;
+  }
+  float4 hi, lo;
+  split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+  char* base = image + (int64_t(t) * n_kb + kb) * (2 * part_bytes(nt));
+  *reinterpret_cast<float4*>(base + c * plane_bytes(nt) + row * 16) = hi;
+  *reinterpret_cast<float4*>(base + part_bytes(nt) + c * plane_bytes(nt) + row * 16) = lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[3], empty_bar[3], acc_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int tile_n = blockIdx.y;
+  const int nt = p.nt;
+  const int S = p.stages;
+  const int stage_sz = stage_bytes(nt);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], kLoaderThreads + 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == kLoaderWarps) {  // TMEM allocation by the MMA warp (whole warp, .sync.aligned)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(uint32_t(p.tmem_cols)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  if (warp < kLoaderWarps) {
+    // =============================== A loaders ===============================
+    const int c = threadIdx.x & 7;           // k-chunk of this thread
+    const int r_base = threadIdx.x >> 3;     // rows r_base + 32*i
+    float4 cur[4], nxt[4];
+    auto issue = [&](int kb, float4(&dst)[4]) {
+      const int k = kb * BK + c * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + r_base + 32 * i;
+        if (m < p.M && k < p.K) dst[i] = __ldg(reinterpret_cast<const float4*>(p.A + int64_t(m) * p.lda + k));
+        else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    issue(0, cur);
+    for (int kb = 0; kb < p.n_kb; ++kb) {
+      const int s = kb % S, use = kb / S;
+      if (kb + 1 < p.n_kb) issue(kb + 1, nxt);
+      if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+      unsigned char* a_hi = smem + s * stage_sz;
+      unsigned char* a_lo = a_hi + part_bytes(BM);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 hi, lo;
+        split4(cur[i], hi, lo);
+        const int off = c * plane_bytes(BM) + (r_base + 32 * i) * 16;
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        *reinterpret_cast<float4*>(a_lo + off) = lo;
+      }
+      fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(&full_bar[s]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+    }
+    // =============================== epilogue ================================
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
+    const int halves = (warp >> 2);                    // 0: low column half, 1: high column half
+    const int row = quarter * 32 + lane;
+    const int m = m0 + row;
+    const int n_tile0 = tile_n * nt;
+    const int groups = nt / 16;                        // 16-column groups in this tile
+    const int g_begin = halves * ((groups + 1) / 2);
+    const int g_end = halves ? groups : (groups + 1) / 2;
+    for (int g = g_begin; g < g_end; ++g) {
+      uint32_t r[16];
+      tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(g * 16), r);
+      if (m >= p.M) continue;
+      const int n_first = n_tile0 + g * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int n = n_first + q * 4;
+        if (n >= p.N) break;
+        float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                               __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+        if (n + 3 < p.N) {
+          if (p.addend) {
+            const float4 a = *reinterpret_cast<const float4*>(p.addend + int64_t(m) * p.ldd + n);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+          }
+          if (p.mask) {
+            const float4 k = *reinterpret_cast<const float4*>(p.mask + int64_t(m) * p.ldm + n);
+            if (!(k.x > 0.f)) v.x = 0.f;
+            if (!(k.y > 0.f)) v.y = 0.f;
+            if (!(k.z > 0.f)) v.z = 0.f;
+            if (!(k.w > 0.f)) v.w = 0.f;
+          }
+          *reinterpret_cast<float4*>(p.C + int64_t(m) * p.ldc + n) = v;
+        } else {
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          for (int e = 0; e < 4 && n + e < p.N; ++e) {
+            float x = vv[e];
+            if (p.addend) x += p.addend[int64_t(m) * p.ldd + n + e];
+            if (p.mask && !(p.mask[int64_t(m) * p.ldm + n + e] > 0.f)) x = 0.f;
+            p.C[int64_t(m) * p.ldc + n + e] = x;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == kLoaderWarps) {
+    // =============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BM, nt);
+      const uint32_t lbo_a = plane_bytes(BM), lbo_b = plane_bytes(nt);
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < p.n_kb; ++kb) {
+        const int s = kb % S, use = kb / S;
+        mbar_wait(&full_bar[s], use & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * stage_sz);
+        const uint32_t a_lo = a_hi + part_bytes(BM);
+        const uint32_t b_hi = a_lo + part_bytes(BM);
+        const uint32_t b_lo = b_hi + part_bytes(nt);
+        const int k_left = p.K - kb * BK;
+        const int ksteps = k_left >= BK ? BK / 8 : (k_left + 7) / 8;
+        for (int j = 0; j < ksteps; ++j) {
+          const uint32_t ao = 2 * j * lbo_a, bo = 2 * j * lbo_b;
+          const uint64_t dah = make_desc(a_hi + ao, lbo_a, 128), dal = make_desc(a_lo + ao, lbo_a, 128);
+          const uint64_t dbh = make_desc(b_hi + bo, lbo_b, 128), dbl = make_desc(b_lo + bo, lbo_b, 128);
+          umma_tf32(tmem_acc, dal, dbh, idesc, accumulate);   // small terms first
+          umma_tf32(tmem_acc, dah, dbl, idesc, 1);
+          umma_tf32(tmem_acc, dah, dbh, idesc, 1);
+          accumulate = 1;
+        }
+        umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
+      }
+      umma_commit(&acc_bar);               // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // =============================== B producer (bulk async copy) ============
+    if (lane == 0) {
+      const uint32_t bytes = 2 * part_bytes(nt);
+      const char* src = p.b_image + int64_t(tile_n) * p.n_kb * bytes;
+      for (int kb = 0; kb < p.n_kb; ++kb) {
+        const int s = kb % S, use = kb / S;
+        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[s], bytes);
+        bulk_g2s(smem + s * stage_sz + 2 * part_bytes(BM), src + int64_t(kb) * bytes, bytes, &full_bar[s]);
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == kLoaderWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(uint32_t(p.tmem_cols)));
+  }
+}
+
+struct Plan {
+  bool ok;
+  int nt, n_tiles, n_kb, stages, tmem_cols;
+  size_t image_bytes, smem_bytes;
+};
+
+static Plan make_plan(int M, int N, int K) {
+  Plan pl{};
+  pl.ok = false;
+  if (M <= 0 || N <= 0 || K <= 0) return pl;
+  const int n16 = (N + 15) / 16 * 16;
+  pl.nt = n16 <= kMaxNt ? n16 : kMaxNt;
+  pl.n_tiles = (N + pl.nt - 1) / pl.nt;
+  pl.n_kb = (K + BK - 1) / BK;
+  pl.stages = pl.nt <= 64 ? 2 : (pl.nt <= 128 ? 3 : 2);
+  if (pl.stages > pl.n_kb) pl.stages = pl.n_kb;
+  pl.tmem_cols = pl.nt <= 32 ? 32 : pl.nt <= 64 ? 64 : pl.nt <= 128 ? 128 : 256;
+  pl.image_bytes = size_t(pl.n_tiles) * pl.n_kb * 2 * part_bytes(pl.nt);
+  pl.smem_bytes = size_t(pl.stages) * stage_bytes(pl.nt);
+  pl.ok = pl.smem_bytes <= 200 * 1024;
+  return pl;
+}
+
+}  // namespace tc
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" size_t gn_tc_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K) {
+  const tc::Plan pl = tc::make_plan(M, N, K);
+  return pl.ok ? align_up(pl.image_bytes) : 0;
+}
+
+extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, const float* B,
+                          int64_t ldb, float* C, int64_t ldc, const float* addend, int64_t ld_addend,
+                          const float* relu_mask, int64_t ld_mask, void* ws, size_t ws_bytes, void* stream) {
+  if (M < 0 || N < 0 || K <= 0 || !A || !B || !C) return GN_ERR_ARG;
+  if (M == 0 || N == 0) return GN_OK;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (!al16(A) || lda % 4 != 0 || K % 4 != 0) return GN_ERR_ARG;            // 128-bit A loads
+  if (!al16(C) || ldc % 4 != 0) return GN_ERR_ARG;                          // 128-bit C stores
+  if (addend && (!al16(addend) || ld_addend % 4 != 0)) return GN_ERR_ARG;
+  if (relu_mask && (!al16(relu_mask) || ld_mask % 4 != 0)) return GN_ERR_ARG;
+  const tc::Plan pl = tc::make_plan(M, N, K);
+  if (!pl.ok) return GN_ERR_ARG;
+  if (!ws || ws_bytes < pl.image_bytes || !al16(ws)) return GN_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int64_t total = int64_t(pl.n_tiles) * pl.n_kb * tc::CHUNKS * pl.nt;
+  GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, B, ldb, transB ? 1 : 0, K, N, pl.nt, pl.n_kb,
+            static_cast<char*>(ws));
+  tc::Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.A = A; p.lda = lda; p.C = C; p.ldc = ldc;
+  p.addend = addend; p.ldd = ld_addend; p.mask = relu_mask; p.ldm = ld_mask;
+  p.b_image = static_cast<const char*>(ws);
+  p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+  static std::atomic<int> attr_set{0};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return GN_ERR_CUDA;
+    }
+    attr_set.store(1, std::memory_order_release);
+  }
+  dim3 grid((unsigned)ceil_div(M, tc::BM), (unsigned)pl.n_tiles);
+  GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
+  return GN_OK;
+}

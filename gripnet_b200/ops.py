@@ -9,6 +9,8 @@ gradients are fused into the producing kernels' epilogues.
 PyTorch is used for device memory (``torch.empty``) and streams only; every
 arithmetic step is a kernel of ``libgripnet_b200.so``.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -89,11 +91,42 @@ def spmm(csr, x, out, F, row_scale=None, bias=None, addend=None, relu=False):
                            int(relu), out.ptr, out.ld, _ptr(partial), _stream()), "gn_spmm")
 
 
+# dense-transform dispatch: "auto" sends tall products (M >= _TC_MIN_M) to the tcgen05 3xTF32 kernel,
+# "ffma" keeps everything on the CUDA-core kernel, "tc" forces the tensor path whenever it is legal
+GEMM_PATH = os.environ.get("GRIPNET_B200_GEMM", "auto")
+_TC_MIN_M = 4096
+
+
+def _tc_eligible(ta, m, n, k, a_ptr, lda, c_ptr, ldc, batch, alpha, accumulate, addend, mask, a_rows):
+    if GEMM_PATH == "ffma" or ta or batch != 1 or a_rows is not None or accumulate or alpha != 1.0:
+        return False
+    if GEMM_PATH != "tc" and (m < _TC_MIN_M or k < 16):
+        return False
+    if k % 4 or lda % 4 or ldc % 4 or a_ptr % 16 or c_ptr % 16 or k > 4096:
+        return False
+    for e in (addend, mask):
+        if e is not None and (e.ld % 4 or e.ptr % 16):
+            return False
+    return True
+
+
 def sgemm(ta, tb, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, device, batch=1, sa=0, sb=0, sc=0, batch_reduce=False,
           alpha=1.0, accumulate=False, addend=None, mask=None, a_rows=None, split_k=True):
-    """C = epilogue(alpha * op(A) op(B)); the library splits the reduction over CTAs when the
-    output alone cannot fill the GPU (deterministic slice-order sum through ``ws``)."""
+    """C = epilogue(alpha * op(A) op(B)).  Tall plain products go to the tcgen05 3xTF32 kernel
+    (``gn_tc_gemm``); everything else to the FFMA kernel, where the library splits the reduction over
+    CTAs when the output alone cannot fill the GPU (deterministic slice-order sum through ``ws``)."""
     lib = _lib.load()
+    if m > 0 and n > 0 and k > 0 and _tc_eligible(ta, m, n, k, a_ptr, lda, c_ptr, ldc, batch, alpha, accumulate,
+                                                  addend, mask, a_rows):
+        nbytes = int(lib.gn_tc_gemm_workspace_bytes(m, n, k))
+        if nbytes:
+            img = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            _lib.check(lib.gn_tc_gemm(int(tb), m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc,
+                                      addend.ptr if addend is not None else None,
+                                      addend.ld if addend is not None else 0,
+                                      mask.ptr if mask is not None else None, mask.ld if mask is not None else 0,
+                                      _ptr(img), nbytes, _stream()), "gn_tc_gemm")
+            return
     ws, ws_bytes = None, 0
     if split_k:
         ws_bytes = int(lib.gn_sgemm_workspace_bytes(m, n, k, batch, int(batch_reduce)))

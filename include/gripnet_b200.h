@@ -175,6 +175,20 @@ int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
              const float* relu_mask, int64_t ld_mask, const int64_t* a_rows,
              int32_t split_k, float* ws, size_t ws_bytes, void* stream);
 
+/* ---- K2/K6 tensor path: tcgen05 (kind::tf32) with 3xTF32 error compensation -- */
+/* C = epilogue( A[M,K] * op(B) ),  op(B) = B [K,N] (transB == 0) or B^T with B stored [N,K].
+ * Each operand element is split hi + lo in TF32 while it is staged and three MMAs per k-step
+ * accumulate lo*hi + hi*lo + hi*hi in one fp32 TMEM accumulator: fp32-grade accuracy
+ * (the 1e-5 parity bar) on the tensor cores.  Requirements: 16-byte aligned A / C / addend /
+ * mask with leading dimensions and K multiples of 4.  `ws` (gn_tc_gemm_workspace_bytes) holds
+ * the pre-split shared-memory image of B.  Epilogue: (+ addend) then zero where relu_mask <= 0.
+ * Replaces torch.matmul at gripnet/layers.py:73 / :181 and its dX transpose for large M. */
+size_t gn_tc_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
+               const float* B, int64_t ldb, float* C, int64_t ldc,
+               const float* addend, int64_t ld_addend, const float* relu_mask, int64_t ld_mask,
+               void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K9/K10: DistMult decoder  ------------------------------------------- */
 /* score_e = sum_k z[src_e,k] z[dst_e,k] w[rel_e,k]; sigmoid optional.
  * Replaces gripnet/decoder.py:19-23 (three [E,D] gathers + two muls + sum). */

@@ -1,0 +1,95 @@
+"""GPU: tcgen05 3xTF32 dense transform (gn_tc_gemm) against a float64 product.
+
+Tolerance: the parity bar of north_star (1e-5 relative, max|a-b|/max|b|) with a margin — the
+error-compensated split must land at fp32-GEMM accuracy (~1e-6), far from plain TF32 (~5e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _tc(tb, A, B, C, addend=None, mask=None):
+    from gripnet_b200 import _lib
+    from gripnet_b200.graph import _ptr, _stream
+    lib = _lib.load()
+    m, k = A.shape
+    n = C.shape[1]
+    nbytes = int(lib.gn_tc_gemm_workspace_bytes(m, n, k))
+    assert nbytes > 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    rc = lib.gn_tc_gemm(int(tb), m, n, k, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), C.data_ptr(),
+                        C.stride(0), _ptr(addend), addend.stride(0) if addend is not None else 0, _ptr(mask),
+                        mask.stride(0) if mask is not None else 0, _ptr(ws), nbytes, _stream())
+    _lib.check(rc, "gn_tc_gemm")
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("tb", [0, 1])
+@pytest.mark.parametrize("m,n,k", [(128, 16, 8), (300, 16, 32), (1000, 64, 128), (4173, 128, 256), (513, 48, 48),
+                                   (2000, 512, 128), (777, 272, 80), (130, 20, 4), (5000, 32, 512), (64, 256, 36)])
+def test_tc_gemm_matches_float64(tb, m, n, k):
+    rs = np.random.RandomState(m + n + k)
+    A = rs.randn(m, k).astype(np.float32)
+    B = rs.randn(k, n).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64)
+    d = _dev()
+    At = torch.from_numpy(A).to(d)
+    Bt = torch.from_numpy(B.T.copy() if tb else B).to(d)
+    C = torch.full((m, n), float("nan"), device=d)
+    _tc(tb, At, Bt, C)
+    err = rel_err(C, want)
+    assert err < 2e-6, err
+
+
+def test_tc_gemm_not_plain_tf32():
+    """Operands with 24 significant bits: a plain-TF32 product would be off by ~1e-3."""
+    d = _dev()
+    rs = np.random.RandomState(0)
+    A = (1.0 + rs.rand(512, 64) * 2 ** -12).astype(np.float32)
+    B = (1.0 + rs.rand(64, 32) * 2 ** -12).astype(np.float32)
+    want = A.astype(np.float64) @ B.astype(np.float64)
+    C = torch.empty(512, 32, device=d)
+    _tc(0, torch.from_numpy(A).to(d), torch.from_numpy(B).to(d), C)
+    diff = (C.double().cpu().numpy() - want)
+    assert np.abs(diff).max() / np.abs(want).max() < 5e-7
+    # and the fine structure is resolved: compare the deviation from the mean product
+    assert np.abs(diff).max() < 0.05 * np.abs(want - want.mean()).max()
+
+
+def test_tc_gemm_epilogue_and_strided_slices():
+    d = _dev()
+    rs = np.random.RandomState(5)
+    m, k, n = 900, 64, 32
+    big_a = torch.from_numpy(rs.randn(m, 96).astype(np.float32)).to(d)       # A = columns 16..80 of a concat buffer
+    A = big_a[:, 16:80]
+    W = torch.from_numpy(rs.randn(k, n).astype(np.float32)).to(d)
+    big_c = torch.zeros(m, 64, device=d)
+    C = big_c[:, 32:64]
+    addend = torch.from_numpy(rs.randn(m, n).astype(np.float32)).to(d)
+    mask = torch.from_numpy(rs.randn(m, n).astype(np.float32)).to(d)
+    _tc(0, A, W, C, addend=addend, mask=mask)
+    want = (A.double() @ W.double() + addend.double()) * (mask > 0).double()
+    assert rel_err(C, want) < 2e-6
+    assert float(big_c[:, :32].abs().sum()) == 0.0                           # nothing written outside the slice
+
+
+def test_dispatch_routes_tall_products_to_tensor_cores():
+    """ops.sgemm sends tall plain products to gn_tc_gemm (2 launches: B image + UMMA kernel)."""
+    import gripnet_b200 as gb
+    from gripnet_b200 import ops
+    d = _dev()
+    m, k, n = 8192, 64, 16
+    A = torch.randn(m, k, device=d)
+    W = torch.randn(k, n, device=d)
+    C = torch.empty(m, n, device=d)
+    before = gb.launch_count()
+    ops.sgemm(False, False, m, n, k, A.data_ptr(), k, W.data_ptr(), n, C.data_ptr(), n, d)
+    assert gb.launch_count() - before == 2
+    assert rel_err(C, A.double() @ W.double()) < 2e-6
