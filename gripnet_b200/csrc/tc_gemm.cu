@@ -53,6 +53,8 @@ struct Params {
   int n_kb;              // k-blocks
   int stages;
   int tmem_cols;
+  int n_acc;             // TMEM accumulators (each covers kb_per_acc k-blocks; summed in fp32 in the epilogue)
+  int kb_per_acc;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -259,6 +261,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
     for (int g = g_begin; g < g_end; ++g) {
       uint32_t r[16];
       tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(g * 16), r);
+      for (int a = 1; a < p.n_acc; ++a) {          // partial accumulators are combined in round-to-nearest fp32
+        uint32_t r2[16];
+        tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(a * nt + g * 16), r2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+      }
       if (m >= p.M) continue;
       const int n_first = n_tile0 + g * 16;
 #pragma unroll
@@ -297,9 +305,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(BM, nt);
       const uint32_t lbo_a = plane_bytes(BM), lbo_b = plane_bytes(nt);
+      // The tensor core truncates when it adds into the fp32 accumulator, so the error of one
+      // accumulator grows linearly with K: long reductions are cut into runs of kb_per_acc
+      // k-blocks, each with its own TMEM accumulator.
       uint32_t accumulate = 0;
       for (int kb = 0; kb < p.n_kb; ++kb) {
         const int s = kb % S, use = kb / S;
+        const uint32_t tmem_d = tmem_acc + uint32_t((kb / p.kb_per_acc) * nt);
+        if (kb % p.kb_per_acc == 0) accumulate = 0;
         mbar_wait(&full_bar[s], use & 1);
         tc_fence_after();
         const uint32_t a_hi = smem_u32(smem + s * stage_sz);
@@ -312,9 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
           const uint32_t ao = 2 * j * lbo_a, bo = 2 * j * lbo_b;
           const uint64_t dah = make_desc(a_hi + ao, lbo_a, 128), dal = make_desc(a_lo + ao, lbo_a, 128);
           const uint64_t dbh = make_desc(b_hi + bo, lbo_b, 128), dbl = make_desc(b_lo + bo, lbo_b, 128);
-          umma_tf32(tmem_acc, dal, dbh, idesc, accumulate);   // small terms first
-          umma_tf32(tmem_acc, dah, dbl, idesc, 1);
-          umma_tf32(tmem_acc, dah, dbh, idesc, 1);
+          umma_tf32(tmem_d, dal, dbh, idesc, accumulate);   // small terms first
+          umma_tf32(tmem_d, dah, dbl, idesc, 1);
+          umma_tf32(tmem_d, dah, dbh, idesc, 1);
           accumulate = 1;
         }
         umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
 
 struct Plan {
   bool ok;
-  int nt, n_tiles, n_kb, stages, tmem_cols;
+  int nt, n_tiles, n_kb, stages, tmem_cols, n_acc, kb_per_acc;
   size_t image_bytes, smem_bytes;
 };
 
@@ -359,7 +372,15 @@ static Plan make_plan(int M, int N, int K) {
   pl.n_kb = (K + BK - 1) / BK;
   pl.stages = pl.nt <= 64 ? 2 : (pl.nt <= 128 ? 3 : 2);
   if (pl.stages > pl.n_kb) pl.stages = pl.n_kb;
-  pl.tmem_cols = pl.nt <= 32 ? 32 : pl.nt <= 64 ? 64 : pl.nt <= 128 ? 128 : 256;
+  pl.kb_per_acc = 4;                                   // 128 k per accumulator
+  pl.n_acc = (pl.n_kb + pl.kb_per_acc - 1) / pl.kb_per_acc;
+  if (pl.n_acc * pl.nt > 512) {                        // TMEM has 512 columns
+    pl.n_acc = 512 / pl.nt;
+    pl.kb_per_acc = (pl.n_kb + pl.n_acc - 1) / pl.n_acc;
+    pl.n_acc = (pl.n_kb + pl.kb_per_acc - 1) / pl.kb_per_acc;
+  }
+  const int cols = pl.n_acc * pl.nt;
+  pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   pl.image_bytes = size_t(pl.n_tiles) * pl.n_kb * 2 * part_bytes(pl.nt);
   pl.smem_bytes = size_t(pl.stages) * stage_bytes(pl.nt);
   pl.ok = pl.smem_bytes <= 200 * 1024;
@@ -399,6 +420,7 @@ extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const flo
   p.addend = addend; p.ldd = ld_addend; p.mask = relu_mask; p.ldm = ld_mask;
   p.b_image = static_cast<const char*>(ws);
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+  p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
   static std::atomic<int> attr_set{0};
   if (!attr_set.load(std::memory_order_acquire)) {
     if (cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {

@@ -1,0 +1,130 @@
+"""GPU: the BASELINE configs at FULL size (configs 1-4), against the CPU oracle port on the same seeded
+inputs and through size-independent properties (CSR invariants, fwd/transpose consistency, linearity of the
+propagation, bit-identical repeat runs).  Tolerance: 1e-5 relative (max|a-b|/max|b|) for embeddings and
+losses, 2e-5 for gradients that sum over hub rows (SURVEY.md §7 "tolerance definition")."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import rel_err
+from oracle import port, synth
+
+pytestmark = pytest.mark.gpu
+TOL, TOL_GRAD = 1e-5, 2e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _compare(model, data, g, p, forward_ref, grads_of=None):
+    from gripnet_b200 import graph as G
+    G.clear_cache()
+    out = model(data)
+    out[0].backward()
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    ref = forward_ref(pl, g)
+    ref[0].backward()
+    assert rel_err(out[0], ref[0]) < TOL, ("loss", rel_err(out[0], ref[0]))
+    assert rel_err(out[1], ref[1]) < TOL, ("z", rel_err(out[1], ref[1]))
+    worst = 0.0
+    for k, v in model.named_parameters():
+        if pl[k].grad is None:
+            assert v.grad is None, k
+            continue
+        e = rel_err(v.grad, pl[k].grad)
+        worst = max(worst, e)
+        assert e < TOL_GRAD, (k, e)
+    # determinism at full size: a second run is bit-identical
+    first = {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None}
+    loss1 = out[0].detach().clone()
+    model.zero_grad(set_to_none=True)
+    out2 = model(data)
+    out2[0].backward()
+    assert torch.equal(out2[0].detach(), loss1)
+    for k, v in model.named_parameters():
+        if v.grad is not None:
+            assert torch.equal(v.grad, first[k]), k
+    return worst
+
+
+def _csr_invariants(graph, n_edges_expected=None):
+    for csr in (graph.fwd, graph.bwd):
+        rp = csr.rowptr.cpu().numpy().astype(np.int64)
+        assert rp[0] == 0 and (np.diff(rp) >= 0).all() and rp[-1] == csr.nnz
+        col = csr.col[: csr.nnz].cpu().numpy()
+        assert col.min() >= 0 and col.max() < csr.n_cols
+    # the transpose CSR holds the same (row, col, val) multiset as the forward CSR
+    f, b = graph.fwd, graph.bwd
+    frow = np.repeat(np.arange(f.n_rows), np.diff(f.rowptr.cpu().numpy()))
+    brow = np.repeat(np.arange(b.n_rows), np.diff(b.rowptr.cpu().numpy()))
+    fcol, bcol = f.col[: f.nnz].cpu().numpy().astype(np.int64), b.col[: b.nnz].cpu().numpy().astype(np.int64)
+    key_f = np.sort(frow * b.n_rows + fcol)
+    key_b = np.sort(bcol * b.n_rows + brow)
+    assert np.array_equal(key_f, key_b)
+    if f.val is not None:
+        assert abs(float(f.val[: f.nnz].double().sum()) - float(b.val[: b.nnz].double().sum())) < 1e-6 * f.nnz
+
+
+def _linearity(graph, F=16):
+    from gripnet_b200 import ops
+    d = _dev()
+    x = torch.randn(graph.fwd.n_cols, F, device=d)
+    y = torch.randn(graph.fwd.n_cols, F, device=d)
+    outs = []
+    for t in (x, y, 2.0 * x - 3.0 * y):
+        o = torch.empty(graph.fwd.n_rows, F, device=d)
+        ops.spmm(graph.fwd, ops.M(t.contiguous()), ops.M(o), F)
+        outs.append(o)
+    assert rel_err(outs[2], 2.0 * outs[0].double() - 3.0 * outs[1].double()) < 1e-5
+    # adjointness: <A x, u> == <x, A^T u>  (forward CSR vs transpose CSR)
+    u = torch.randn(graph.fwd.n_rows, F, device=d)
+    atu = torch.empty(graph.bwd.n_rows, F, device=d)
+    ops.spmm(graph.bwd, ops.M(u), ops.M(atu), F)
+    lhs = float((outs[0].double() * u.double()).sum())
+    rhs = float((x.double() * atu.double()).sum())
+    assert abs(lhs - rhs) < 1e-6 * max(abs(lhs), abs(rhs), 1.0)
+
+
+def test_config1_pose0_full():
+    from gripnet_b200.pipelines import PoseModel, load_flat_params, to_device
+    g = synth.pose_graph()
+    p = synth.pose_params(g)
+    m = load_flat_params(PoseModel(g["n_g"], g["n_d"], g["n_rel"]), p).to(_dev())
+    _compare(m, to_device(g, _dev()), g, p, port.pose_forward)
+    gg = m.gg.conv_list[0]._graph
+    assert gg.nnz == g["gg_edge_index"].shape[1] - int((g["gg_edge_index"][0] == g["gg_edge_index"][1]).sum()) + g["n_g"]
+    _csr_invariants(gg)
+    _linearity(gg)
+
+
+def test_config2_aminer_full():
+    from gripnet_b200.pipelines import AminerModel, load_flat_params, to_device
+    g = synth.aminer_full()
+    p = synth.aminer_params(g)
+    m = load_flat_params(AminerModel(g["n_p"], g["n_a"], g["n_class"]), p).to(_dev())
+    _compare(m, to_device(g, _dev()), g, p, port.aminer_forward)
+    _csr_invariants(m.pp.conv_list[0]._graph)
+    _csr_invariants(m.pa.conv._graph)
+    _linearity(m.aa.conv_list[0]._graph, F=64)
+
+
+def test_config3_freebase_d_full():
+    from gripnet_b200.pipelines import FreebaseDModel, load_flat_params, to_device
+    g = synth.freebase_d_full()
+    p = synth.freebase_d_params(g)
+    m = load_flat_params(FreebaseDModel(g["n_p"], g["n_q"], g["n_a"], g["n_class"]), p).to(_dev())
+    _compare(m, to_device(g, _dev()), g, p, port.freebase_d_forward)
+    _csr_invariants(m.qq.conv_list[0]._graph)
+    _linearity(m.pp.conv_list[0]._graph, F=128)
+
+
+def test_config4_pose2_many_relations():
+    """R = 1097 relation types, power-law sizes, E_dd ~ 8.3 M: relation-batched transform + segmented conv."""
+    from gripnet_b200.pipelines import PoseModel, load_flat_params, to_device
+    sizes = synth.pose2_rel_sizes()
+    g = synth.pose_graph(n_rel=len(sizes), rel_sizes=sizes)
+    assert g["n_rel"] == 1097 and g["dd_edge_index"].shape[1] > 8_000_000
+    p = synth.pose_params(g)
+    m = load_flat_params(PoseModel(g["n_g"], g["n_d"], g["n_rel"]), p).to(_dev())
+    _compare(m, to_device(g, _dev()), g, p, port.pose_forward)

@@ -33,7 +33,7 @@ def _tc(tb, A, B, C, addend=None, mask=None):
 
 @pytest.mark.parametrize("tb", [0, 1])
 @pytest.mark.parametrize("m,n,k", [(128, 16, 8), (300, 16, 32), (1000, 64, 128), (4173, 128, 256), (513, 48, 48),
-                                   (2000, 512, 128), (777, 272, 80), (130, 20, 4), (5000, 32, 512), (64, 256, 36)])
+                                   (2000, 512, 128), (777, 272, 80), (130, 20, 4), (5000, 32, 512), (64, 256, 36), (3000, 128, 1024), (1500, 256, 640)])
 def test_tc_gemm_matches_float64(tb, m, n, k):
     rs = np.random.RandomState(m + n + k)
     A = rs.randn(m, k).astype(np.float32)
@@ -45,7 +45,8 @@ def test_tc_gemm_matches_float64(tb, m, n, k):
     C = torch.full((m, n), float("nan"), device=d)
     _tc(tb, At, Bt, C)
     err = rel_err(C, want)
-    assert err < 2e-6, err
+    # one TMEM accumulator covers <= 128 k (<= 320 k when N = 256 leaves room for only two accumulators)
+    assert err < (2e-6 if k <= 256 else 4e-6), err
 
 
 def test_tc_gemm_not_plain_tf32():
