@@ -148,14 +148,21 @@ __global__ void __launch_bounds__(kLossThreads) lp_loss_partial_kernel(const flo
   }
 }
 
+// one warp: lane l adds partials l, l+32, ... in order, then a fixed shuffle tree (deterministic)
 __global__ void lp_loss_final_kernel(const float* __restrict__ ws, int n_blocks, int64_t n_pos, int64_t n_neg,
                                      float* __restrict__ loss) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int lane = threadIdx.x;
   float a = 0.f, b = 0.f;
-  for (int i = 0; i < n_blocks; ++i) {
+  for (int i = lane; i < n_blocks; i += 32) {
     a += ws[2 * i];
     b += ws[2 * i + 1];
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(kFull, a, off);
+    b += __shfl_xor_sync(kFull, b, off);
+  }
+  if (lane != 0) return;
   const float lp = n_pos > 0 ? -(a / float(n_pos)) : 0.f;
   const float ln = n_neg > 0 ? -(b / float(n_neg)) : 0.f;
   loss[0] = lp + ln;
@@ -183,10 +190,12 @@ __global__ void __launch_bounds__(kLossThreads) nc_loss_partial_kernel(const flo
 }
 
 __global__ void nc_loss_final_kernel(const float* __restrict__ ws, int n_blocks, int64_t n, float* __restrict__ loss) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int lane = threadIdx.x;
   float a = 0.f;
-  for (int i = 0; i < n_blocks; ++i) a += ws[i];
-  loss[0] = n > 0 ? -(a / float(n)) : 0.f;
+  for (int i = lane; i < n_blocks; i += 32) a += ws[i];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(kFull, a, off);
+  if (lane == 0) loss[0] = n > 0 ? -(a / float(n)) : 0.f;
 }
 
 __global__ void nc_loss_bwd_kernel(const float* __restrict__ score, int64_t n, int C,

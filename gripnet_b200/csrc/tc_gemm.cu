@@ -5,8 +5,11 @@
 // Why: north_star item 3 sends the dense X.W / X.W_r feature transforms to tcgen05, but
 // the parity bar is 1e-5 relative in fp32 and a TF32 operand keeps 10 mantissa bits.
 // Every operand element is split  x = hi + lo  (hi = rna-tf32(x), lo = rna-tf32(x - hi))
-// while it is staged, and each k-step issues three MMAs into the same fp32 accumulator:
-// lo*hi + hi*lo + hi*hi (the lo*lo term, <= 2^-22 relative, is dropped).
+// while it is staged, and each k-step issues three MMAs: hi*hi into the main fp32 accumulator,
+// lo*hi + hi*lo into a second one (the lo*lo term, <= 2^-22 relative, is dropped).  The tensor
+// core TRUNCATES when it adds into the accumulator, so the small cross terms get their own
+// TMEM columns (their truncation error is 2^-11 of the main one's) and the main accumulator
+// takes one add per k-step instead of three; the two are summed in fp32 in the epilogue.
 //
 // Shape regime: M = number of nodes (huge), K <= 512, N <= 512 (feature widths).  These
 // products are HBM-bound (read A once, write C once), so the kernel is built around the
@@ -53,7 +56,7 @@ struct Params {
   int n_kb;              // k-blocks
   int stages;
   int tmem_cols;
-  int n_acc;             // TMEM accumulators (each covers kb_per_acc k-blocks; summed in fp32 in the epilogue)
+  int n_acc;             // TMEM accumulator PAIRS (hi*hi | cross terms); each covers kb_per_acc k-blocks
   int kb_per_acc;
 };
 
@@ -259,11 +262,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
     const int g_begin = halves * ((groups + 1) / 2);
     const int g_end = halves ? groups : (groups + 1) / 2;
     for (int g = g_begin; g < g_end; ++g) {
+      // cross-term accumulators first (small), then the hi*hi ones: round-to-nearest fp32 adds
       uint32_t r[16];
-      tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(g * 16), r);
-      for (int a = 1; a < p.n_acc; ++a) {          // partial accumulators are combined in round-to-nearest fp32
+      tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(p.n_acc * nt + g * 16), r);
+      for (int a = 1; a < 2 * p.n_acc; ++a) {
+        const int col = (a < p.n_acc ? p.n_acc + a : a - p.n_acc) * nt + g * 16;
         uint32_t r2[16];
-        tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(a * nt + g * 16), r2);
+        tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(col), r2);
 #pragma unroll
         for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
       }
@@ -307,11 +312,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
       const uint32_t lbo_a = plane_bytes(BM), lbo_b = plane_bytes(nt);
       // The tensor core truncates when it adds into the fp32 accumulator, so the error of one
       // accumulator grows linearly with K: long reductions are cut into runs of kb_per_acc
-      // k-blocks, each with its own TMEM accumulator.
+      // k-blocks, each with its own TMEM accumulator pair.
       uint32_t accumulate = 0;
       for (int kb = 0; kb < p.n_kb; ++kb) {
         const int s = kb % S, use = kb / S;
-        const uint32_t tmem_d = tmem_acc + uint32_t((kb / p.kb_per_acc) * nt);
+        const uint32_t tmem_d = tmem_acc + uint32_t((kb / p.kb_per_acc) * nt);              // hi*hi
+        const uint32_t tmem_x = tmem_acc + uint32_t((p.n_acc + kb / p.kb_per_acc) * nt);    // lo*hi + hi*lo
         if (kb % p.kb_per_acc == 0) accumulate = 0;
         mbar_wait(&full_bar[s], use & 1);
         tc_fence_after();
@@ -325,9 +331,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
           const uint32_t ao = 2 * j * lbo_a, bo = 2 * j * lbo_b;
           const uint64_t dah = make_desc(a_hi + ao, lbo_a, 128), dal = make_desc(a_lo + ao, lbo_a, 128);
           const uint64_t dbh = make_desc(b_hi + bo, lbo_b, 128), dbl = make_desc(b_lo + bo, lbo_b, 128);
-          umma_tf32(tmem_d, dal, dbh, idesc, accumulate);   // small terms first
-          umma_tf32(tmem_d, dah, dbl, idesc, 1);
-          umma_tf32(tmem_d, dah, dbh, idesc, 1);
+          umma_tf32(tmem_x, dal, dbh, idesc, accumulate);
+          umma_tf32(tmem_x, dah, dbl, idesc, 1);
+          umma_tf32(tmem_d, dah, dbh, idesc, accumulate);
           accumulate = 1;
         }
         umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
@@ -374,12 +380,12 @@ static Plan make_plan(int M, int N, int K) {
   if (pl.stages > pl.n_kb) pl.stages = pl.n_kb;
   pl.kb_per_acc = 4;                                   // 128 k per accumulator
   pl.n_acc = (pl.n_kb + pl.kb_per_acc - 1) / pl.kb_per_acc;
-  if (pl.n_acc * pl.nt > 512) {                        // TMEM has 512 columns
-    pl.n_acc = 512 / pl.nt;
+  if (2 * pl.n_acc * pl.nt > 512) {                    // TMEM has 512 columns; two accumulators per run
+    pl.n_acc = 256 / pl.nt;
     pl.kb_per_acc = (pl.n_kb + pl.n_acc - 1) / pl.n_acc;
     pl.n_acc = (pl.n_kb + pl.kb_per_acc - 1) / pl.kb_per_acc;
   }
-  const int cols = pl.n_acc * pl.nt;
+  const int cols = 2 * pl.n_acc * pl.nt;
   pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   pl.image_bytes = size_t(pl.n_tiles) * pl.n_kb * 2 * part_bytes(pl.nt);
   pl.smem_bytes = size_t(pl.stages) * stage_bytes(pl.nt);

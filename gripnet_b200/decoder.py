@@ -26,6 +26,12 @@ class multiRelaInnerProductDecoder(Module):
     def forward(self, z, edge_index, edge_type, sigmoid=True):
         return ops.DistMult.apply(z, replicated(self.weight, self.dist_ctx), edge_index, edge_type, bool(sigmoid))
 
+    def score_pair(self, z, pos_edge_index, neg_edge_index, edge_type, sigmoid=True):
+        """``(forward(z, pos, et), forward(z, neg, et))`` of one training step
+        (``GripNet-pose.py:133-138``) as one autograd node whose two halves run concurrently."""
+        return ops.DistMultPair.apply(z, replicated(self.weight, self.dist_ctx), pos_edge_index, neg_edge_index,
+                                      edge_type, bool(sigmoid))
+
     def reset_parameters(self):
         with torch.no_grad():
             self.weight.normal_(std=1.0 / math.sqrt(self.in_dim))          # decoder.py:25-26

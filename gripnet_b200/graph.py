@@ -11,13 +11,25 @@ from collections import OrderedDict
 
 import torch
 
-from . import _lib
+from . import _lib, streams
 
 _SM_COUNT = 148
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """The CUDA stream every kernel launch goes to: the active side branch (``streams.py``) or
+    torch's current stream."""
+    s = streams.override()
+    return (s if s is not None else torch.cuda.current_stream()).cuda_stream
+
+
+def _host_int(t):
+    """One device int -> host (a build-time sync).  Inside a side branch the producing kernels are not
+    ordered before a copy on torch's current stream, so that stream is drained first."""
+    s = streams.override()
+    if s is not None:
+        s.synchronize()
+    return int(t.item())
 
 
 def _ptr(t):
@@ -35,7 +47,9 @@ def require_cuda(t, name, dtype=None):
 
 
 def _ws(nbytes, device):
-    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    streams.keep(t)          # scratch of a side-stream launch lives until the branch joins
+    return t
 
 
 def pick_chunk_len(nnz):
@@ -67,13 +81,26 @@ class Csr:
                                        _ptr(self.chunk_row), _ptr(self.chunk_beg), cap, _ptr(self.row_counter),
                                        _ptr(ws), ws.numel(), _stream()), "gn_build_chunks")
         if exact:   # one host read at graph-build time (never inside a captured step)
-            self.n_chunks = int(self.chunk_ptr[self.n_rows].item()) if self.n_rows > 0 else 0
+            self.n_chunks = _host_int(self.chunk_ptr[self.n_rows]) if self.n_rows > 0 else 0
         else:
             self.n_chunks = cap - 1 if self.n_rows > 0 else 0
         self.c = _lib.GnCsr(self.n_rows, self.n_cols, self.nnz, self.chunk_len, self.n_chunks, 0,
                             _ptr(rowptr), _ptr(col), _ptr(val), _ptr(self.chunk_ptr), _ptr(self.chunk_row),
                             _ptr(self.chunk_beg), _ptr(self.row_counter))
         self.ref = C.byref(self.c)
+        self._alt = None
+
+    def alt_ref(self):
+        """The same CSR with a second set of row-arrival counters, so that two kernels may walk it
+        concurrently on different streams (``ops.DistMultPair``: dw of the positive and of the negative
+        edges share the relation CSR)."""
+        if self._alt is None:
+            rc = torch.zeros(max(self.n_rows, 1), dtype=torch.int32, device=self.rowptr.device)
+            c = _lib.GnCsr(self.n_rows, self.n_cols, self.nnz, self.chunk_len, self.n_chunks, 0,
+                           _ptr(self.rowptr), _ptr(self.col), _ptr(self.val), _ptr(self.chunk_ptr),
+                           _ptr(self.chunk_row), _ptr(self.chunk_beg), _ptr(rc))
+            self._alt = (c, C.byref(c), rc)
+        return self._alt[1]
 
     @property
     def extra_chunks(self):
@@ -83,7 +110,9 @@ class Csr:
         """Scratch for rows split over several chunks (2 slots per extra chunk), or None."""
         if self.extra_chunks == 0:
             return None
-        return torch.empty(2 * self.extra_chunks * int(width), dtype=torch.float32, device=self.rowptr.device)
+        t = torch.empty(2 * self.extra_chunks * int(width), dtype=torch.float32, device=self.rowptr.device)
+        streams.keep(t)
+        return t
 
 
 class GcnGraph:
@@ -136,7 +165,7 @@ class GcnGraph:
             _ptr(aug_norm), _ptr(rowptr), _ptr(col), _ptr(val), _ptr(perm), _ptr(rowptr_t), _ptr(col_t),
             _ptr(val_t), _ptr(perm_t), _ptr(self.deg), _ptr(self.indeg), _ptr(counts), _ptr(ws), ws.numel(),
             _stream()), "gn_gcn_prep")
-        self.nnz = int(counts[0].item())           # E' (one host read, at graph-build time)
+        self.nnz = _host_int(counts[0])            # E' (one host read, at graph-build time)
         self.perm, self.perm_t = perm[: self.nnz], perm_t[: self.nnz]
         self.fwd = Csr(rowptr, col, val, n_dst, n_src, self.nnz)
         self.bwd = Csr(rowptr_t, col_t, val_t, n_src, n_dst, self.nnz)

@@ -13,7 +13,7 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, streams
 from .graph import _ptr, _stream, _ws, require_cuda
 
 EPS = 1e-13  # reference gripnet/utils.py:10
@@ -120,7 +120,7 @@ def sgemm(ta, tb, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, device, batch=1, 
                                                   addend, mask, a_rows):
         nbytes = int(lib.gn_tc_gemm_workspace_bytes(m, n, k))
         if nbytes:
-            img = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            img = _ws(nbytes, device)
             _lib.check(lib.gn_tc_gemm(int(tb), m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc,
                                       addend.ptr if addend is not None else None,
                                       addend.ld if addend is not None else 0,
@@ -132,6 +132,7 @@ def sgemm(ta, tb, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, device, batch=1, 
         ws_bytes = int(lib.gn_sgemm_workspace_bytes(m, n, k, batch, int(batch_reduce)))
         if ws_bytes:
             ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=device)
+            streams.keep(ws)
     _lib.check(lib.gn_sgemm(int(ta), int(tb), m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, batch, sa, sb, sc,
                             int(batch_reduce), float(alpha), int(accumulate),
                             addend.ptr if addend is not None else None, addend.ld if addend is not None else 0,
@@ -234,6 +235,8 @@ class GcnStack(torch.autograd.Function):
         grads = [None] * (2 * n_layers)
         dz_slot = None            # set when `dh` already is a masked dZ living in a gatherable slot
         dx0 = None
+        # bias / weight gradients leave the dependency chain dZ -> dY -> dH_{l-1}: side stream
+        br = streams.Branch(enabled=dctx is None)
         for l in range(n_layers, 0, -1):
             f, k = dims[l], dims[l - 1]
             h_l, h_prev = outs[l], outs[l - 1]
@@ -250,14 +253,17 @@ class GcnStack(torch.autograd.Function):
                 dz.m, dz.full, dz.dctx = dh, dh, None
             if ctx.has_bias[l - 1] and ctx.needs_input_grad[4 + 2 * (l - 1) + 1]:
                 db = torch.empty(f, dtype=torch.float32, device=dev)
-                colsum(dz.m, db)
+                with br(dz.m.t):
+                    colsum(dz.m, db)
                 grads[2 * (l - 1) + 1] = _reduce(dctx, db)
             dy = M(_new(graph.n_src, f, g))
             spmm(graph.bwd, dz.gather(), dy, f)
             if ctx.needs_input_grad[4 + 2 * (l - 1)]:
                 dw = torch.empty((k, f), dtype=torch.float32, device=dev)
                 # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
-                sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f, dev)
+                with br(dy.t, h_prev.t):
+                    sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f,
+                          dev)
                 grads[2 * (l - 1)] = _reduce(dctx, dw)
             need_prev = (l > 1) or ctx.needs_input_grad[0]
             dz_slot = None
@@ -275,6 +281,7 @@ class GcnStack(torch.autograd.Function):
                     dz_slot = dprev
                 if l == 1:
                     dx0 = dprev.m.t
+        br.join()
         return (dx0, None, None, None) + tuple(grads)
 
 
@@ -366,6 +373,7 @@ class RgcnStack(torch.autograd.Function):
         grads = [None] * (4 * n_layers)
         dz_slot = None
         dx0 = None
+        br = streams.Branch(enabled=dctx is None)      # parameter gradients off the dZ -> dY -> dH chain
         for l in range(n_layers, 0, -1):
             f, k = dims[l], dims[l - 1]
             w, bs, at, rt = ws_list[l - 1]
@@ -386,29 +394,34 @@ class RgcnStack(torch.autograd.Function):
             base = 4 + 4 * (l - 1)
             if ctx.has_bias[l - 1] and ctx.needs_input_grad[base + 3]:
                 db = torch.empty(f, dtype=torch.float32, device=dev)
-                colsum(dz, db)
+                with br(dz.t):
+                    colsum(dz, db)
                 grads[4 * (l - 1) + 3] = _reduce(dctx, db)
             # dY[(j,r)] = sum_{e: src=j, rel=r} dZ[dst_e] / c_dst   (transpose CSR, atomic-free)
             dy = torch.empty((n * r, f), dtype=torch.float32, device=dev)
             spmm(graph.bwd, dzs.gather(), M(dy), f)
             if ctx.needs_input_grad[base + 2]:
                 droot = torch.empty((k, f), dtype=torch.float32, device=dev)
-                sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev)
+                with br(dz.t, h_prev.t):
+                    sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev)
                 grads[4 * (l - 1) + 2] = _reduce(dctx, droot)
             if ctx.needs_input_grad[base] or ctx.needs_input_grad[base + 1]:
                 # dW[r] = H_{l-1}^T dY[:, r, :]
                 dw = torch.empty((r, k, f), dtype=torch.float32, device=dev)
-                sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dy.data_ptr(), r * f, dw.data_ptr(), f, dev,
-                      batch=r, sa=0, sb=f, sc=k * f)
-                if ctx.needs_input_grad[base + 1]:
-                    datt = torch.empty((r, nb), dtype=torch.float32, device=dev)
-                    sgemm(False, True, r, nb, k * f, dw.data_ptr(), k * f, bs.data_ptr(), k * f, datt.data_ptr(), nb,
-                          dev)
+                datt = torch.empty((r, nb), dtype=torch.float32, device=dev) if ctx.needs_input_grad[base + 1] else None
+                dbasis = torch.empty((nb, k, f), dtype=torch.float32, device=dev) if ctx.needs_input_grad[base] else None
+                with br(dy, h_prev.t, dw, bs, at):
+                    sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dy.data_ptr(), r * f, dw.data_ptr(), f, dev,
+                          batch=r, sa=0, sb=f, sc=k * f)
+                    if datt is not None:
+                        sgemm(False, True, r, nb, k * f, dw.data_ptr(), k * f, bs.data_ptr(), k * f, datt.data_ptr(),
+                              nb, dev)
+                    if dbasis is not None:
+                        sgemm(True, False, nb, k * f, r, at.data_ptr(), nb, dw.data_ptr(), k * f, dbasis.data_ptr(),
+                              k * f, dev)
+                if datt is not None:
                     grads[4 * (l - 1) + 1] = _reduce(dctx, datt)
-                if ctx.needs_input_grad[base]:
-                    dbasis = torch.empty((nb, k, f), dtype=torch.float32, device=dev)
-                    sgemm(True, False, nb, k * f, r, at.data_ptr(), nb, dw.data_ptr(), k * f, dbasis.data_ptr(),
-                          k * f, dev)
+                if dbasis is not None:
                     grads[4 * (l - 1)] = _reduce(dctx, dbasis)
             need_prev = (l > 1) or ctx.needs_input_grad[0]
             dz_slot = None
@@ -426,6 +439,7 @@ class RgcnStack(torch.autograd.Function):
                     dz_slot = dps
                 if l == 1:
                     dx0 = dprev.t
+        br.join()
         return (dx0, None, None, None) + tuple(grads)
 
 
@@ -506,25 +520,67 @@ class InterTail(torch.autograd.Function):
 # ----------------------------------------------------------------------------
 # DistMult decoder  (decoder.py:19-23)
 # ----------------------------------------------------------------------------
+def _distmult_check(z, weight, edge_index, edge_type):
+    z = _as_rows(z, "z")
+    w = _as_rows(weight, "weight").contiguous()
+    require_cuda(edge_index, "edge_index", torch.int64)
+    require_cuda(edge_type, "edge_type", torch.int64)
+    if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_type.numel() != edge_index.size(1):
+        raise RuntimeError("edge_index must be [2,E] and edge_type [E]")
+    if w.size(1) != z.size(1):
+        raise RuntimeError("decoder weight width must equal the embedding width")
+    return z, w, edge_index.contiguous(), edge_type.contiguous()
+
+
+def _distmult_fwd(z, w, ei, et, sigmoid):
+    e = ei.size(1)
+    out = torch.empty(e, dtype=torch.float32, device=z.device)
+    _lib.check(_lib.load().gn_distmult_fwd(z.data_ptr(), z.stride(0) if z.size(0) > 1 else z.size(1), z.size(1),
+                                           w.data_ptr(), _ptr(ei[0]) if e else None, _ptr(ei[1]) if e else None,
+                                           _ptr(et) if e else None, e, int(sigmoid), _ptr(out), _stream()),
+               "gn_distmult_fwd")
+    return out
+
+
+def _distmult_coef(g, out, sigmoid):
+    e = out.numel()
+    coef = torch.empty(max(e, 1), dtype=torch.float32, device=out.device)
+    _lib.check(_lib.load().gn_distmult_coef(_ptr(g), _ptr(out), e, int(sigmoid), _ptr(coef), _stream()),
+               "gn_distmult_coef")
+    return coef
+
+
+def _distmult_dz(key_tensors, coef, z, w):
+    """dz[i] = sum over the endpoint-CSR row of node i of coef_e * z[other] * w[rel]  (atomic-free)."""
+    from .graph import edge_struct
+    n, d, r = z.size(0), z.size(1), w.size(0)
+    es = edge_struct(key_tensors[0], key_tensors[1], n, r)
+    dz = torch.empty((n, d), dtype=torch.float32, device=z.device)
+    part = es.node.partial(d)
+    _lib.check(_lib.load().gn_distmult_bwd_z(es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid),
+                                             _ptr(coef), z.data_ptr(), z.stride(0) if n > 1 else d, d, w.data_ptr(),
+                                             dz.data_ptr(), d, _ptr(part), _stream()), "gn_distmult_bwd_z")
+    return dz
+
+
+def _distmult_dw(dw, edge_type_key, ei, coef, z, alt=False):
+    """dw[r] = sum over the relation-CSR row r of coef_e * z[src_e] * z[dst_e], into the caller's ``dw``.
+    ``alt``: use the CSR's second set of arrival counters (a concurrent walk of the same CSR)."""
+    from .graph import rel_struct
+    n, d, r, e = z.size(0), z.size(1), dw.size(0), ei.size(1)
+    rs = rel_struct(edge_type_key, r)
+    part = rs.csr.partial(d)
+    _lib.check(_lib.load().gn_distmult_bwd_w(rs.csr.alt_ref() if alt else rs.csr.ref, _ptr(rs.perm), _ptr(ei[0]) if e else None,
+                                             _ptr(ei[1]) if e else None, _ptr(coef), z.data_ptr(),
+                                             z.stride(0) if n > 1 else d, d, dw.data_ptr(), _ptr(part), _stream()),
+               "gn_distmult_bwd_w")
+
+
 class DistMult(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, weight, edge_index, edge_type, sigmoid):
-        lib = _lib.load()
-        z = _as_rows(z, "z")
-        w = _as_rows(weight, "weight").contiguous()
-        require_cuda(edge_index, "edge_index", torch.int64)
-        require_cuda(edge_type, "edge_type", torch.int64)
-        if edge_index.dim() != 2 or edge_index.size(0) != 2 or edge_type.numel() != edge_index.size(1):
-            raise RuntimeError("edge_index must be [2,E] and edge_type [E]")
-        if w.size(1) != z.size(1):
-            raise RuntimeError("decoder weight width must equal the embedding width")
-        ei, et = edge_index.contiguous(), edge_type.contiguous()
-        e = ei.size(1)
-        out = torch.empty(e, dtype=torch.float32, device=z.device)
-        _lib.check(lib.gn_distmult_fwd(z.data_ptr(), z.stride(0) if z.size(0) > 1 else z.size(1), z.size(1),
-                                       w.data_ptr(), _ptr(ei[0]) if e else None, _ptr(ei[1]) if e else None,
-                                       _ptr(et) if e else None, e, int(sigmoid), _ptr(out), _stream()),
-                   "gn_distmult_fwd")
+        z, w, ei, et = _distmult_check(z, weight, edge_index, edge_type)
+        out = _distmult_fwd(z, w, ei, et, sigmoid)
         ctx.sigmoid = bool(sigmoid)
         ctx.key_tensors = (edge_index, edge_type)
         ctx.save_for_backward(z, w, out, ei, et)
@@ -532,32 +588,75 @@ class DistMult(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
-        from .graph import edge_struct, rel_struct
-        lib = _lib.load()
         z, w, out, ei, et = ctx.saved_tensors
-        n, d, r, e = z.size(0), z.size(1), w.size(0), ei.size(1)
-        dev = z.device
-        g = grad.contiguous()
-        ldz = z.stride(0) if n > 1 else d
-        coef = torch.empty(max(e, 1), dtype=torch.float32, device=dev)
-        _lib.check(lib.gn_distmult_coef(_ptr(g), _ptr(out), e, int(ctx.sigmoid), _ptr(coef), _stream()),
-                   "gn_distmult_coef")
+        coef = _distmult_coef(grad.contiguous(), out, ctx.sigmoid)
         dz = dw = None
+        br = streams.Branch()
+        if ctx.needs_input_grad[1]:                      # dw next to dz: they only share `coef`
+            dw = torch.empty_like(w)
+            with br(coef, z, ei):
+                _distmult_dw(dw, ctx.key_tensors[1], ei, coef, z)
         if ctx.needs_input_grad[0]:
-            es = edge_struct(ctx.key_tensors[0], ctx.key_tensors[1], n, r)
-            dz = torch.empty((n, d), dtype=torch.float32, device=dev)
-            part = es.node.partial(d)
-            _lib.check(lib.gn_distmult_bwd_z(es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid),
-                                             _ptr(coef), z.data_ptr(), ldz, d, w.data_ptr(), dz.data_ptr(), d,
-                                             _ptr(part), _stream()), "gn_distmult_bwd_z")
-        if ctx.needs_input_grad[1]:
-            rs = rel_struct(ctx.key_tensors[1], r)
-            dw = torch.empty((r, d), dtype=torch.float32, device=dev)
-            part = rs.csr.partial(d)
-            _lib.check(lib.gn_distmult_bwd_w(rs.csr.ref, _ptr(rs.perm), _ptr(ei[0]) if e else None,
-                                             _ptr(ei[1]) if e else None, _ptr(coef), z.data_ptr(), ldz, d,
-                                             dw.data_ptr(), _ptr(part), _stream()), "gn_distmult_bwd_w")
+            dz = _distmult_dz(ctx.key_tensors, coef, z, w)
+        br.join()
         return dz, dw, None, None, None
+
+
+class DistMultPair(torch.autograd.Function):
+    """Positive and negative edge lists of one training step scored together
+    (``GripNet-pose.py:133-138`` calls the decoder twice on the same ``z`` and ``edge_type``).
+
+    Same kernels as two ``DistMult`` calls; the two lists are independent, so forward runs them on two
+    streams and backward on four (dz_pos | dz_neg | dw_pos | dw_neg; the two dw walk the shared relation
+    CSR with separate arrival counters), then ``dz = dz_pos + dz_neg`` and ``dw = dw_pos + dw_neg`` in
+    that fixed order — the same sums autograd forms for two separate calls.
+    """
+
+    @staticmethod
+    def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid):
+        z, w, pi, et = _distmult_check(z, weight, pos_index, edge_type)
+        _, _, ni, _ = _distmult_check(z, weight, neg_index, edge_type)
+        br = streams.Branch()
+        with br(z, w, ni, et):
+            neg = _distmult_fwd(z, w, ni, et, sigmoid)
+        pos = _distmult_fwd(z, w, pi, et, sigmoid)
+        br.join()
+        ctx.sigmoid = bool(sigmoid)
+        ctx.keys = (pos_index, neg_index, edge_type)
+        ctx.save_for_backward(z, w, pos, neg, pi, ni, et)
+        return pos, neg
+
+    @staticmethod
+    def backward(ctx, g_pos, g_neg):
+        z, w, pos, neg, pi, ni, et = ctx.saved_tensors
+        pos_key, neg_key, et_key = ctx.keys
+        need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        b_neg, b_wp = streams.Branch(), streams.Branch()
+        g_pos, g_neg = g_pos.contiguous(), g_neg.contiguous()
+        coef_p = _distmult_coef(g_pos, pos, ctx.sigmoid)
+        dz = dz_n = dw = dw_n = None
+        if need_w:
+            dw, dw_n = torch.empty_like(w), torch.empty_like(w)
+            with b_wp(coef_p, z, pi):
+                _distmult_dw(dw, et_key, pi, coef_p, z)
+        with b_neg(g_neg, neg, z, w):
+            coef_n = _distmult_coef(g_neg, neg, ctx.sigmoid)
+            b_wn = streams.Branch()                     # forks off b_neg's stream, behind coef_n
+            if need_w:
+                with b_wn(coef_n, z, ni):
+                    _distmult_dw(dw_n, et_key, ni, coef_n, z, alt=True)
+            if need_z:
+                dz_n = _distmult_dz((neg_key, et_key), coef_n, z, w)
+        if need_z:
+            dz = _distmult_dz((pos_key, et_key), coef_p, z, w)
+        b_wn.join()
+        b_neg.join()
+        if need_z:
+            axpby(M(dz), 1.0, M(dz_n), 1.0, M(dz))
+        b_wp.join()
+        if need_w:
+            axpby(M(dw), 1.0, M(dw_n), 1.0, M(dw))
+        return dz, dw, None, None, None, None
 
 
 # ----------------------------------------------------------------------------

@@ -40,8 +40,7 @@ class PoseModel(Module):
         dctx = data.get("dist")
         if dctx is None:
             neg = data["neg_edge_index"] if neg_edge_index is None else neg_edge_index
-            pos_score = self.dmt(z, data["dd_edge_index"], data["dd_edge_type"])
-            neg_score = self.dmt(z, neg, data["dd_edge_type"])
+            pos_score, neg_score = self.dmt.score_pair(z, data["dd_edge_index"], neg, data["dd_edge_type"])
             return link_prediction_loss(pos_score, neg_score), z, pos_score, neg_score
         neg = data["neg_edge_index_local"] if neg_edge_index is None else neg_edge_index
         z_full = parallel.all_gather_rows(z, dctx, data["n_d_global"])

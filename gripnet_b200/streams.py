@@ -1,0 +1,122 @@
+"""Fork / join of side streams inside one training step.
+
+At pose-0 size a step is ~70 kernels of 3-50 us, most of them latency-bound at 10-30 %
+occupancy (``profiles/r01_v4_ncu_full_summary.csv``), and about half of the summed kernel time
+is OFF the critical path: weight / bias gradients (``X^T dY``, column sums), the decoder's
+``dw`` next to its ``dz``, the negative edges' decoder next to the positive ones.  A ``Branch``
+sends such kernels to a side stream so they overlap the dependency chain; when the step is
+captured (``capture.py``) the fork / join events become parallel branches of the CUDA graph.
+
+Rules that keep this safe with PyTorch's caching allocator (which only orders reuse of a block on
+the stream that allocated it):
+
+* torch's *current* stream is never switched: every tensor is still allocated on the caller's
+  stream; only the kernels launched inside ``with branch(...)`` go to the side stream
+  (``graph._stream()`` honours the override);
+* every entry into the branch re-forks: the side stream waits for everything enqueued on the
+  caller's stream so far, so a block the allocator recycled is no longer in use there;
+* every tensor a side kernel reads or scratches — the ones passed to ``branch(...)`` and all
+  temporaries allocated while the branch is active (``keep``) — is held until ``join()``, after which the
+  caller's stream is ordered behind the side work and normal stream-ordered reuse is safe again;
+* results are allocated by the caller (on its stream) and must not be consumed before ``join()``.
+
+Branches nest (a branch created inside ``with other:`` forks off that side stream and hands its
+temporaries to the parent on ``join``).  Partitioned (multi-GPU) runs do not branch: their
+collectives are issued on the caller's stream.
+"""
+import os
+import threading
+
+import torch
+
+ENABLED = os.environ.get("GRIPNET_B200_STREAMS", "1") != "0"
+_N_SIDE = 4
+_tls = threading.local()
+_pools = {}
+_pool_lock = threading.Lock()
+
+
+def override():
+    """The torch.cuda.Stream kernels are redirected to, or None."""
+    return getattr(_tls, "side", None)
+
+
+def effective_stream():
+    s = override()
+    return s if s is not None else torch.cuda.current_stream()
+
+
+def keep(*tensors):
+    """Hold temporaries of a side-stream launch until the active branch joins (no-op otherwise)."""
+    b = getattr(_tls, "branch", None)
+    if b is not None:
+        b._keep.extend(t for t in tensors if t is not None)
+
+
+def _next_side(device, avoid=None):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    with _pool_lock:
+        pool = _pools.get(idx)
+        if pool is None:
+            pool = _pools[idx] = [[torch.cuda.Stream(device=idx) for _ in range(_N_SIDE)], 0]
+        for _ in range(_N_SIDE):
+            pool[1] = (pool[1] + 1) % _N_SIDE
+            if avoid is None or pool[0][pool[1]].cuda_stream != avoid.cuda_stream:
+                break
+        return pool[0][pool[1]]
+
+
+class Branch:
+    """One side stream forked off the caller's stream.
+
+        br = Branch()
+        out = torch.empty(...)                  # allocated by the caller
+        with br(x, y):                          # x, y: tensors the side kernels read
+            launch_kernels(x, y, out)           # -> side stream
+        ...                                     # the caller's stream carries on
+        br.join()                               # before `out` is consumed / returned
+    """
+
+    def __init__(self, enabled=True):
+        self.enabled = bool(enabled) and ENABLED
+        self._keep = []
+        self._dirty = False
+        self._args = ()
+        self._parent = getattr(_tls, "branch", None)     # created inside another branch: nested fork
+        if self.enabled:
+            self.main = effective_stream()
+            self.side = _next_side(self.main.device, avoid=self.main)
+
+    def __call__(self, *tensors):
+        self._args = tensors
+        return self
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        self._keep.extend(t for t in self._args if t is not None)
+        self._args = ()
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        self.side.wait_event(ev)
+        self._prev = (getattr(_tls, "side", None), getattr(_tls, "branch", None))
+        _tls.side, _tls.branch = self.side, self
+        self._dirty = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            _tls.side, _tls.branch = self._prev
+        return False
+
+    def join(self):
+        if self.enabled and self._dirty:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.main.wait_event(ev)
+            self._dirty = False
+        if self._parent is not None:
+            # only the parent's side stream is ordered behind this branch so far: the temporaries stay
+            # alive until the parent joins the stream that allocated them
+            self._parent._keep.extend(self._keep)
+        self._keep.clear()

@@ -29,16 +29,25 @@ def _neg_pairs(rs, pos, n_nodes, count):
 
 
 def pose_graph(n_g=19081, gg_pairs=715612, n_d=645, e_gd=18596, n_rel=16, dd_pairs_per_rel=12500,
-               seed=1111, weighted=False, rel_sizes=None):
-    """pose-shaped supergraph (config 1; config 4 via ``n_rel`` / ``rel_sizes``)."""
+               seed=1111, weighted=False, rel_sizes=None, pair_pool=None):
+    """pose-shaped supergraph (config 1; config 4 via ``n_rel`` / ``rel_sizes`` / ``pair_pool``).
+
+    ``pair_pool``: every relation draws its drug pairs from one fixed pool of that many random
+    pairs instead of from all ``n_d**2`` (the pose datasets hold ~63 k interacting drug pairs and
+    each side effect occurs on a subset of them).  Needed when ``E_dd >> n_d**2``: uniform pairs
+    would make every pair a positive and leave no negative to sample."""
     rs = np.random.RandomState(seed)
     gg = _mirror(rs.randint(0, n_g, size=(2, gg_pairs)).astype(np.int64))
     gd = np.stack([rs.randint(0, n_g, size=e_gd), rs.randint(0, n_d, size=e_gd)]).astype(np.int64)
     if rel_sizes is None:
         rel_sizes = [dd_pairs_per_rel] * n_rel
     chunks, ranges, start = [], [], 0
+    pool = None if pair_pool is None else rs.randint(0, n_d, size=(2, int(pair_pool))).astype(np.int64)
     for k in rel_sizes:
-        e = _mirror(rs.randint(0, n_d, size=(2, int(k))).astype(np.int64))
+        if pool is None:
+            e = _mirror(rs.randint(0, n_d, size=(2, int(k))).astype(np.int64))
+        else:
+            e = _mirror(pool[:, rs.randint(0, pool.shape[1], size=int(k))])
         chunks.append(e)
         ranges.append((start, start + e.shape[1]))   # get_range_list, gripnet/utils.py:141-148
         start += e.shape[1]
@@ -180,6 +189,13 @@ def pose2_rel_sizes(n_rel=1097, total_pairs=4_150_000, min_pairs=450, seed=1111)
     rs.shuffle(w)
     sizes = np.maximum(min_pairs, (w / w.sum() * total_pairs).astype(np.int64))
     return sizes.tolist()
+
+
+def pose2_graph(seed=1111):
+    """BASELINE config 4 (pose-2-shaped): R = 1097 relations with power-law sizes, E_dd ~ 8.3 M directed
+    edges over a pool of 63 473 drug pairs."""
+    sizes = pose2_rel_sizes(seed=seed)
+    return pose_graph(n_rel=len(sizes), rel_sizes=sizes, pair_pool=63473, seed=seed)
 
 
 def aminer_small(seed=1111):

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from gripnet_b200.synthetic import (  # noqa: F401
-    aminer_full, aminer_small, freebase_d_full, freebase_d_small, nc_graph, pose2_rel_sizes,
+    aminer_full, aminer_small, freebase_d_full, freebase_d_small, nc_graph, pose2_graph, pose2_rel_sizes,
     pose_edges_per_epoch, pose_graph, pose_medium, pose_small)
 
 

@@ -1,7 +1,8 @@
 """GPU: the BASELINE configs at FULL size (configs 1-4), against the CPU oracle port on the same seeded
 inputs and through size-independent properties (CSR invariants, fwd/transpose consistency, linearity of the
 propagation, bit-identical repeat runs).  Tolerance: 1e-5 relative (max|a-b|/max|b|) for embeddings and
-losses, 2e-5 for gradients that sum over hub rows (SURVEY.md §7 "tolerance definition")."""
+losses, 2e-5 for gradients that sum over hub rows (SURVEY.md §7 "tolerance definition"); gradients are
+compared with the ReLU branch pattern pinned (see ``_compare``)."""
 import numpy as np
 import pytest
 import torch
@@ -17,16 +18,36 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _compare(model, data, g, p, forward_ref, grads_of=None):
+def _compare(model, data, g, p, forward_ref, modules):
+    """Forward (loss, z) against the unmodified oracle; gradients against the oracle with the ReLU branch
+    pattern pinned to the one the device took (oracle/port.py:_relu explains why: at these sizes a few
+    pre-activations lie within fp32 rounding of zero, and fp32-vs-fp64 runs of the ORACLE ITSELF then
+    differ by 4e-3 on the embedding gradient)."""
     from gripnet_b200 import graph as G
     G.clear_cache()
+    seen = {}
+    hooks = [getattr(model, n).register_forward_hook(lambda mod, a, o, n=n: seen.__setitem__(n, o.detach().cpu()))
+             for n in modules]
     out = model(data)
     out[0].backward()
-    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    ref = forward_ref(pl, g)
-    ref[0].backward()
+    for h in hooks:
+        h.remove()
+    assert sorted(seen) == sorted(modules)
+    with torch.no_grad():
+        ref = forward_ref(p, g)
     assert rel_err(out[0], ref[0]) < TOL, ("loss", rel_err(out[0], ref[0]))
     assert rel_err(out[1], ref[1]) < TOL, ("z", rel_err(out[1], ref[1]))
+    # the branch patterns may only disagree where the activation is ~0
+    zd, zr = out[1].detach().cpu(), ref[1]
+    flip = (zd > 0) != (zr > 0)
+    if bool(flip.any()):
+        assert float(torch.maximum(zd.abs(), zr.abs())[flip].max()) < TOL * float(zr.abs().max())
+    # float64 oracle for the gradients: with R ~ 10^3 relations one relation sums ~5e5 terms, where the
+    # fp32 oracle's own sequential index_add is the less accurate side (1.6e-4 on dmt.weight at config 4)
+    pl = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    refp = forward_ref(pl, g, patterns=seen)
+    refp[0].backward()
+    assert rel_err(out[0], refp[0]) < TOL and rel_err(out[1], refp[1]) < TOL
     worst = 0.0
     for k, v in model.named_parameters():
         if pl[k].grad is None:
@@ -91,7 +112,7 @@ def test_config1_pose0_full():
     g = synth.pose_graph()
     p = synth.pose_params(g)
     m = load_flat_params(PoseModel(g["n_g"], g["n_d"], g["n_rel"]), p).to(_dev())
-    _compare(m, to_device(g, _dev()), g, p, port.pose_forward)
+    _compare(m, to_device(g, _dev()), g, p, port.pose_forward, ("gg", "gd", "dd"))
     gg = m.gg.conv_list[0]._graph
     assert gg.nnz == g["gg_edge_index"].shape[1] - int((g["gg_edge_index"][0] == g["gg_edge_index"][1]).sum()) + g["n_g"]
     _csr_invariants(gg)
@@ -103,7 +124,7 @@ def test_config2_aminer_full():
     g = synth.aminer_full()
     p = synth.aminer_params(g)
     m = load_flat_params(AminerModel(g["n_p"], g["n_a"], g["n_class"]), p).to(_dev())
-    _compare(m, to_device(g, _dev()), g, p, port.aminer_forward)
+    _compare(m, to_device(g, _dev()), g, p, port.aminer_forward, ("pp", "pa", "aa"))
     _csr_invariants(m.pp.conv_list[0]._graph)
     _csr_invariants(m.pa.conv._graph)
     _linearity(m.aa.conv_list[0]._graph, F=64)
@@ -114,7 +135,7 @@ def test_config3_freebase_d_full():
     g = synth.freebase_d_full()
     p = synth.freebase_d_params(g)
     m = load_flat_params(FreebaseDModel(g["n_p"], g["n_q"], g["n_a"], g["n_class"]), p).to(_dev())
-    _compare(m, to_device(g, _dev()), g, p, port.freebase_d_forward)
+    _compare(m, to_device(g, _dev()), g, p, port.freebase_d_forward, ("pp", "pa", "qq", "qa", "aa"))
     _csr_invariants(m.qq.conv_list[0]._graph)
     _linearity(m.pp.conv_list[0]._graph, F=128)
 
@@ -122,9 +143,8 @@ def test_config3_freebase_d_full():
 def test_config4_pose2_many_relations():
     """R = 1097 relation types, power-law sizes, E_dd ~ 8.3 M: relation-batched transform + segmented conv."""
     from gripnet_b200.pipelines import PoseModel, load_flat_params, to_device
-    sizes = synth.pose2_rel_sizes()
-    g = synth.pose_graph(n_rel=len(sizes), rel_sizes=sizes)
+    g = synth.pose2_graph()
     assert g["n_rel"] == 1097 and g["dd_edge_index"].shape[1] > 8_000_000
     p = synth.pose_params(g)
     m = load_flat_params(PoseModel(g["n_g"], g["n_d"], g["n_rel"]), p).to(_dev())
-    _compare(m, to_device(g, _dev()), g, p, port.pose_forward)
+    _compare(m, to_device(g, _dev()), g, p, port.pose_forward, ("gg", "gd", "dd"))

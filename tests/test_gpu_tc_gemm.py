@@ -59,7 +59,9 @@ def test_tc_gemm_not_plain_tf32():
     C = torch.empty(512, 32, device=d)
     _tc(0, torch.from_numpy(A).to(d), torch.from_numpy(B).to(d), C)
     diff = (C.double().cpu().numpy() - want)
-    assert np.abs(diff).max() / np.abs(want).max() < 5e-7
+    # all-positive sums are the worst case of the tensor core's TRUNCATING fp32 accumulate (a bias of about
+    # half an ulp per hi*hi MMA, 8 of them here); plain TF32 would be ~2e-4
+    assert np.abs(diff).max() / np.abs(want).max() < 1e-6
     # and the fine structure is resolved: compare the deviation from the mean product
     assert np.abs(diff).max() < 0.05 * np.abs(want - want.mean()).max()
 

@@ -204,3 +204,30 @@ def test_dense64_agrees_on_pose_stages():
     assert rel_err(z, c["out"]["z"]) < TOL
     pos = dense64.distmult(z, p["dmt.weight"], g["dd_edge_index"], g["dd_edge_type"])
     assert rel_err(pos, c["out"]["pos"]) < TOL
+
+
+def test_pinned_relu_pattern_is_the_identity_on_the_oracles_own_pattern():
+    """oracle/port.py:_relu — replaying the branch pattern the oracle itself took changes nothing
+    (this is the hook the full-size GPU gradient tests use)."""
+    from oracle import port, synth
+    g = synth.pose_small()
+    p = synth.pose_params(g)
+    sub = port._sub
+    with torch.no_grad():
+        z_gg = port.homo_forward(sub(p, "gg."), None, g["gg_edge_index"], if_catout=True)
+        z_gd = port.inter_forward(sub(p, "gd."), z_gg, g["gd_edge_index"], g["n_d"], mod="cat", if_relu=True)
+        z_dd = port.homo_forward(sub(p, "dd."), z_gd, g["dd_edge_index"], edge_type=g["dd_edge_type"],
+                                 range_list=g["dd_range_list"], if_catout=True, multi_relational=True)
+    res = []
+    for patterns in (None, {"gg": z_gg, "gd": z_gd, "dd": z_dd}):
+        pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+        out = port.pose_forward(pl, g, patterns=patterns)
+        out[0].backward()
+        res.append((out, pl))
+    assert torch.equal(res[0][0][1], z_dd)
+    assert torch.allclose(res[0][0][0], res[1][0][0], rtol=0, atol=0)
+    for k in p:
+        a, b = res[0][1][k].grad, res[1][1][k].grad
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert torch.equal(a, b), k
