@@ -423,10 +423,13 @@ def run_cuda(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if args.workload == "pose" else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
             "config": {"workload": w["desc"], "edges_per_step": e_epoch,
                        "parallelism": "single GPU" if world == 1 else
-                       f"destination-partitioned x{world}: NCCL all-gather of SpMM operands, all-reduce of weight grads",
+                       f"destination-partitioned x{world}: SpMM operands exchanged by " +
+                       ("gn_peer_allgather (P2P stores into the peers' symmetric-memory gather buffers over NVLink)"
+                        if dctx.arena is not None else "NCCL all-gather") + ", NCCL all-reduce of weight grads",
                        "l2": "flushed between timed steps (write of a 252 MiB buffer, outside the event pair)",
                        "execution": execution},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": w["h2d_bytes"],

@@ -70,6 +70,8 @@ SIGNATURES = {
     "gn_lp_loss_bwd": (_INT, [_P, _I64, _P, _I64, _F, _P, _P, _P, _P]),
     "gn_nc_loss_fwd": (_INT, [_P, _I64, _I32, _P, _F, _P, _P, _SZ, _P]),
     "gn_nc_loss_bwd": (_INT, [_P, _I64, _I32, _P, _F, _P, _P, _P]),
+    "gn_peer_max_world": (_INT, []),
+    "gn_peer_allgather": (_INT, [_P, _I32, _I32, _I64, _I64, _I64, _I32, _P, _P, _P, _P]),
 }
 
 EW_COPY, EW_ABS, EW_RELU, EW_ADD = 0, 1, 2, 3

@@ -63,7 +63,7 @@ class Slot:
             t = _new(n_local, f, like)
             self.m, self.full = M(t), M(t)
         else:
-            buf = _new(dctx.world * block, f, like)
+            buf = dctx.slot_buffer(dctx.world * block, f, like)
             self.full = M(buf)
             self.m = M(buf[dctx.rank * block: dctx.rank * block + n_local])
 
@@ -235,8 +235,9 @@ class GcnStack(torch.autograd.Function):
         grads = [None] * (2 * n_layers)
         dz_slot = None            # set when `dh` already is a masked dZ living in a gatherable slot
         dx0 = None
-        # bias / weight gradients leave the dependency chain dZ -> dY -> dH_{l-1}: side stream
-        br = streams.Branch(enabled=dctx is None)
+        # bias / weight gradients leave the dependency chain dZ -> dY -> dH_{l-1}: side stream (a partitioned
+        # run all-reduces them on the caller's stream right away unless the reduction is deferred)
+        br = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce)
         for l in range(n_layers, 0, -1):
             f, k = dims[l], dims[l - 1]
             h_l, h_prev = outs[l], outs[l - 1]
@@ -373,7 +374,7 @@ class RgcnStack(torch.autograd.Function):
         grads = [None] * (4 * n_layers)
         dz_slot = None
         dx0 = None
-        br = streams.Branch(enabled=dctx is None)      # parameter gradients off the dZ -> dY -> dH chain
+        br = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce)   # parameter gradients off the chain
         for l in range(n_layers, 0, -1):
             f, k = dims[l], dims[l - 1]
             w, bs, at, rt = ws_list[l - 1]

@@ -19,8 +19,68 @@ identity), after which the ordinary drop-in modules (``homoGraph``, ``interGraph
 with LOCAL node counts — run the partitioned path.  ``torch.distributed`` does the plumbing; all
 arithmetic stays in the library's kernels.
 """
+import ctypes
+import os
+import sys
+
 import torch
 import torch.distributed as dist
+
+PEER_MODE = os.environ.get("GRIPNET_B200_PEER", "auto")     # "auto" | "off"
+
+
+class PeerArena:
+    """Symmetric device arena mapped by every rank of the node (torch symmetric memory: CUDA VMM
+    allocation + peer mapping over NVLink) from which the SpMM gather buffers are carved, so that
+    ``gn_peer_allgather`` can push slots straight into the peers' buffers.
+
+    Layout (identical on every rank): ``[flag block | data]``.  ``alloc`` is a bump allocator reset at
+    every step; all ranks run the same sequence of allocations, so a buffer has the same offset — and
+    the same flag index — everywhere."""
+    MAX_BUFFERS = 1024
+
+    def __init__(self, dctx, data_bytes):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        lib = _lib.load()
+        self.max_world = int(lib.gn_peer_max_world())
+        if dctx.world > self.max_world:
+            raise RuntimeError("peer all-gather supports at most %d ranks" % self.max_world)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.flag_bytes = self.MAX_BUFFERS * self.max_world * 8
+        self.capacity = int(data_bytes)
+        self.t = symm.empty(self.flag_bytes + self.capacity, dtype=torch.uint8, device=dev)
+        group = dctx.group if dctx.group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.t, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(ptrs) != dctx.world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        self.bases = (ctypes.c_uint64 * dctx.world)(*ptrs)
+        self.t[: self.flag_bytes].zero_()
+        self.seq = torch.zeros(self.MAX_BUFFERS, dtype=torch.int64, device=dev)
+        self.done = torch.zeros(self.MAX_BUFFERS, dtype=torch.int32, device=dev)
+        self.abort = torch.zeros(1, dtype=torch.int32, device=dev)      # raised by a timed-out wait
+        self.off = 0
+        self.index = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=dctx.group)
+
+    def reset(self):
+        self.off = 0
+        self.index = 0
+
+    def alloc(self, nbytes):
+        """-> (uint8 view of the local arena, byte offset in the arena, buffer index) or None when full."""
+        nbytes = int(nbytes)
+        padded = (nbytes + 255) // 256 * 256
+        if self.off + padded > self.capacity or self.index >= self.MAX_BUFFERS:
+            return None
+        start = self.flag_bytes + self.off
+        view = self.t[start:start + nbytes]
+        tok = (view, start, self.index)
+        self.off += padded
+        self.index += 1
+        return tok
 
 
 class DistContext:
@@ -37,6 +97,14 @@ class DistContext:
         # all-reduce after ``backward()`` with ``reduce_gradients`` (fewer, larger collectives).
         self.defer_grad_reduce = bool(defer_grad_reduce)
         self._bucket = None
+        # peer-memory exchange (PeerArena): sized from the first step, which still runs on NCCL
+        self.peer_mode = PEER_MODE if self.world > 1 else "off"
+        self.arena = None
+        self._tokens = {}
+        self._step_bytes = 0
+        self._step_gathers = 0
+        self.peer_gathers = 0            # statistics: gathers served by gn_peer_allgather / by NCCL
+        self.nccl_gathers = 0
 
     # ---- block partition -------------------------------------------------
     def block(self, n):
@@ -60,13 +128,79 @@ class DistContext:
         """Contiguous slice of an edge list of length ``e`` scored by this rank."""
         return block_bounds(e, self.world, self.rank if rank is None else rank)
 
+    # ---- peer-memory gather buffers -----------------------------------------
+    def begin_step(self):
+        """Call once at the start of every training step (the model containers in ``pipelines.py`` do).
+        Rewinds the arena's bump allocator; after the first step — whose gather buffers came from the
+        ordinary allocator and were exchanged with NCCL while their sizes were recorded — it creates the
+        symmetric arena (a collective: every rank takes the same decision from the same shapes)."""
+        if self.peer_mode != "auto":
+            return
+        if self.arena is None and self._step_bytes > 0:
+            if self._step_gathers >= 2:           # buffer-reuse argument of peer.cu needs >= 2 gathers per step
+                self._create_arena(self._step_bytes)
+            else:
+                self.peer_mode = "off"
+        if self.arena is not None:
+            self.arena.reset()
+        self._tokens.clear()
+        self._step_bytes = 0
+        self._step_gathers = 0
+
+    def _create_arena(self, data_bytes):
+        ok = torch.ones(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        arena = None
+        try:
+            arena = PeerArena(self, data_bytes)
+        except Exception as e:                    # no symmetric memory on this system: keep NCCL
+            sys.stderr.write(f"gripnet_b200: peer all-gather disabled on rank {self.rank} ({type(e).__name__}: {e})\n")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self.arena = arena
+        else:
+            self.peer_mode = "off"
+
+    def peer_failed(self):
+        """True if a peer-memory gather timed out (one host read; call outside captured regions)."""
+        return self.arena is not None and int(self.arena.abort.item()) != 0
+
+    def slot_buffer(self, rows, f, like):
+        """A ``[rows, f]`` fp32 gather buffer (``rows = world * B``): from the symmetric arena when it
+        exists (then ``all_gather_slots`` exchanges it over peer memory), else from the allocator."""
+        nbytes = int(rows) * int(f) * 4
+        if self.peer_mode == "auto":
+            self._step_bytes += (nbytes + 255) // 256 * 256
+            self._step_gathers += 1
+            if self.arena is not None and (nbytes // self.world) % 16 == 0 and nbytes % self.world == 0:
+                tok = self.arena.alloc(nbytes)
+                if tok is not None:
+                    t = tok[0].view(torch.float32).view(int(rows), int(f))
+                    self._tokens[t.data_ptr()] = tok
+                    return t
+        return torch.empty((rows, f), dtype=torch.float32, device=like.device)
+
     # ---- collectives -----------------------------------------------------
     def all_gather_slots(self, full):
-        """``full`` is ``[world*B, F]`` with this rank's slot already written: complete it in place."""
+        """``full`` is ``[world*B, F]`` with this rank's slot already written: complete it in place —
+        over NVLink peer memory (``gn_peer_allgather``) for arena buffers, with NCCL otherwise."""
         if self.world == 1:
+            return full
+        tok = self._tokens.get(full.data_ptr())
+        if tok is not None:
+            from . import _lib
+            from .graph import _stream
+            a = self.arena
+            _, offset, index = tok
+            slot_bytes = full.numel() * 4 // self.world
+            _lib.check(_lib.load().gn_peer_allgather(a.bases, self.world, self.rank, offset, slot_bytes, 0, index,
+                                                     a.seq[index:].data_ptr(), a.done[index:].data_ptr(),
+                                                     a.abort.data_ptr(), _stream()), "gn_peer_allgather")
+            self.peer_gathers += 1
             return full
         b = full.size(0) // self.world
         dist.all_gather_into_tensor(full, full[self.rank * b:(self.rank + 1) * b], group=self.group)
+        self.nccl_gathers += 1
         return full
 
     def all_reduce_(self, t):

@@ -36,8 +36,10 @@ class PoseModel(Module):
 
         Partitioned run (``data`` from ``shard_pose``): ``z`` holds this rank's drug rows, the scores
         are those of this rank's slice of the edge lists, the loss is the global mean."""
-        z = self.embed(data)
         dctx = data.get("dist")
+        if dctx is not None:
+            dctx.begin_step()
+        z = self.embed(data)
         if dctx is None:
             neg = data["neg_edge_index"] if neg_edge_index is None else neg_edge_index
             pos_score, neg_score = self.dmt.score_pair(z, data["dd_edge_index"], neg, data["dd_edge_type"])
@@ -104,6 +106,8 @@ class ChainModel(Module):
         self.mcip = multiClassInnerProductDecoder(3 * hid + out, n_class)
 
     def forward(self, data):
+        if data.get("dist") is not None:
+            data["dist"].begin_step()
         z = self.aa(None, data["aa_edge_index"], if_catout=True)
         z = self.ab(z, data["ab_edge_index"], if_relu=True, mod="cat")
         z = self.bb(z, data["bb_edge_index"], if_catout=True)

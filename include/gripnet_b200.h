@@ -247,6 +247,24 @@ int gn_nc_loss_fwd(const float* score, int64_t n, int32_t C, const int64_t* labe
 int gn_nc_loss_bwd(const float* score, int64_t n, int32_t C, const int64_t* label, float eps,
                    const float* grad_loss /*[1]*/, float* grad_score, void* stream);
 
+/* ---- K12: slot all-gather over NVLink peer memory (multi-GPU exchange step) ------------------ */
+/* New design (the reference is single-device).  Every rank of the node maps one
+ * symmetric arena of identical layout; `arena_base` (HOST array, `world` entries) holds every rank's
+ * arena base as this process sees it (peer-mapped device pointers).  The gather buffer is
+ * [world][slot_bytes] at `buf_offset` of every arena; this rank's slot is already written.  The call
+ * pushes the slot to every peer (128-bit P2P stores), publishes flag (flag_index, rank) = use counter
+ * in every peer's flag block (u64 [n_buffers][gn_peer_max_world()] at `flag_offset`, zero-initialised)
+ * and waits until all peers have published theirs: kernels enqueued after it on `stream` see the
+ * complete buffer.  `seq` / `done`: this buffer's LOCAL use counter (u64) and CTA arrival counter
+ * (u32), zero-initialised, owned by the caller; `abort_flag` (u32, zero-initialised, shared by all
+ * buffers) is raised when a wait times out (~10 s: a peer died) — later calls then do not wait and the
+ * host should treat the step as failed.  Every rank must issue the same sequence of calls.
+ * slot_bytes and buf_offset must be multiples of 16.  world == 1 is a no-op. */
+int gn_peer_max_world(void);
+int gn_peer_allgather(const uint64_t* arena_base /*host*/, int32_t world, int32_t rank, int64_t buf_offset,
+                      int64_t slot_bytes, int64_t flag_offset, int32_t flag_index, uint64_t* seq,
+                      uint32_t* done, uint32_t* abort_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,47 @@ def run_chain(dctx, dev):
     return worst
 
 
+def run_peer(dctx, dev):
+    """Peer-memory exchange (gn_peer_allgather over the symmetric arena) against the NCCL exchange:
+    step 1 runs on NCCL (the arena is sized from it), steps 2.. push slots over NVLink peer memory.
+    The gather is a copy and every kernel is deterministic, so all steps must agree BIT FOR BIT —
+    eagerly and when the step is replayed from a CUDA graph."""
+    from gripnet_b200 import graph as G
+    from gripnet_b200.capture import CapturedStep
+    from gripnet_b200.pipelines import PoseModel, load_flat_params, shard_pose, shard_pose_params
+    from oracle import synth
+    g = synth.pose_medium()
+    p = synth.pose_params(g)
+    G.clear_cache()
+    data = shard_pose(g, dctx, dev)
+    m = load_flat_params(PoseModel(data["n_g"], data["n_d"], g["n_rel"]), shard_pose_params(p, g, dctx)).to(dev)
+    m.dmt.dist_ctx = dctx
+    snaps = []
+    side = torch.cuda.Stream()           # not the legacy stream: the same model is captured below
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for step in range(3):
+            m.zero_grad(set_to_none=True)
+            loss, z, pos, neg = m(data)
+            loss.backward()
+            torch.cuda.synchronize()
+            snaps.append([loss.detach().clone(), z.detach().clone()] +
+                         [v.grad.clone() for v in m.parameters() if v.grad is not None])
+    torch.cuda.synchronize()
+    used_peer = dctx.peer_gathers > 0
+    assert not dctx.peer_failed(), "a peer gather timed out"
+    for a, b in zip(snaps[0], snaps[2]):
+        assert torch.equal(a, b), "peer-memory exchange differs from the NCCL exchange"
+    # captured + replayed
+    step = CapturedStep(lambda: m(data), m.parameters(), warmup=1)
+    for _ in range(3):
+        out = step.replay()
+    torch.cuda.synchronize()
+    assert not dctx.peer_failed()
+    assert torch.equal(out[0].detach(), snaps[0][0]) and torch.equal(out[1].detach(), snaps[0][1])
+    return used_peer, dctx.peer_gathers, dctx.nccl_gathers
+
+
 def main():
     import gripnet_b200  # noqa: F401
     from gripnet_b200.parallel import DistContext
@@ -129,11 +170,18 @@ def main():
     w1 = run_pose(dctx, dev, with_oracle=(rank == 0))
     w2 = run_chain(dctx, dev)
     w1 = max(w1, run_pose(DistContext(defer_grad_reduce=True), dev, with_oracle=False))
+    peer = (False, 0, 0)
+    if world > 1:
+        peer = run_peer(DistContext(), dev)
     t = torch.tensor([w1, w2], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"dist_worker: world={world} OK  worst rel err pose {float(t[0]):.2e}  chain {float(t[1]):.2e}", flush=True)
-    dist.destroy_process_group()
+        print(f"dist_worker: world={world} OK  worst rel err pose {float(t[0]):.2e}  chain {float(t[1]):.2e}  "
+              f"peer-memory exchange {'ON' if peer[0] else 'off'} ({peer[1]} peer / {peer[2]} nccl gathers)", flush=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)          # captured graphs hold NCCL work: skip the communicator teardown (see bench.py)
 
 
 if __name__ == "__main__":
