@@ -179,11 +179,13 @@ class GcnStack(torch.autograd.Function):
         dctx = getattr(graph, "ctx", None)
         b_src = graph.b_src if dctx is not None else None
         outs = []      # M views of H_0 .. H_L
+        br = streams.Branch(enabled=dctx is None)
         if catout:
             buf = _new(graph.n_dst, sum(dims), x0)
             offs = [sum(dims[:i]) for i in range(len(dims))]
             h0 = M(buf, offs[0], dims[0])
-            map2d(_lib.EW_COPY, M(x0), h0)
+            with br(x0):                         # the concat copy of H_0 is off the chain: layer 0 reads x0 itself
+                map2d(_lib.EW_COPY, M(x0), h0)
             outs.append(h0)
         else:
             buf = None
@@ -192,7 +194,7 @@ class GcnStack(torch.autograd.Function):
             w = weights[l].contiguous()
             k, f = dims[l], dims[l + 1]
             y = Slot(graph.n_src, f, x0, dctx, b_src)
-            xin = outs[l]
+            xin = M(x0) if l == 0 else outs[l]
             sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, y.m.ld, dev)
             if catout:
                 hl = M(buf, offs[l + 1], f)
@@ -201,6 +203,7 @@ class GcnStack(torch.autograd.Function):
             b = biases[l].contiguous() if biases[l] is not None else None
             spmm(graph.fwd, y.gather(), hl, f, bias=b, relu=relu_flags[l])
             outs.append(hl)
+        br.join()
         ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
         ctx.has_bias = [b is not None for b in biases]
         ws = [w.contiguous() for w in weights]
@@ -307,11 +310,13 @@ class RgcnStack(torch.autograd.Function):
         dctx = getattr(graph, "ctx", None)
         blk = graph.b if dctx is not None else None
         outs, ws_list = [], []
+        br = streams.Branch(enabled=dctx is None)
         if catout:
             buf = _new(n, sum(dims), x0)
             offs = [sum(dims[:i]) for i in range(len(dims))]
             h0 = M(buf, offs[0], dims[0])
-            map2d(_lib.EW_COPY, M(x0), h0)
+            with br(x0):
+                map2d(_lib.EW_COPY, M(x0), h0)
             outs.append(h0)
         else:
             buf = None
@@ -325,20 +330,24 @@ class RgcnStack(torch.autograd.Function):
             # W[r] = sum_b att[r,b] basis[b]   (layers.py:172-173)
             w = torch.empty((r, k, f), dtype=torch.float32, device=dev)
             sgemm(False, False, r, k * f, nb, at.data_ptr(), nb, bs.data_ptr(), k * f, w.data_ptr(), k * f, dev)
-            xin = outs[l]
+            xin = M(x0) if l == 0 else outs[l]
+            hl = M(buf, offs[l + 1], f) if catout else M(_new(n, f, x0))
+            # root term X root (layers.py:193), next to the relation transforms; the segmented mean
+            # accumulates onto it
+            with br(xin.t, rt, hl.t):
+                sgemm(False, False, n, f, k, xin.ptr, xin.ld, rt.data_ptr(), f, hl.ptr, hl.ld, dev)
             # Y[:, r, :] = X W[r] for every relation at once (transform-then-gather)
             y = Slot(n, r * f, x0, dctx, blk)
             sgemm(False, False, n, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, r * f, dev,
                   batch=r, sa=0, sb=k * f, sc=f)
-            hl = M(buf, offs[l + 1], f) if catout else M(_new(n, f, x0))
-            # root term first, then the segmented mean accumulates onto it (layers.py:193)
-            sgemm(False, False, n, f, k, xin.ptr, xin.ld, rt.data_ptr(), f, hl.ptr, hl.ld, dev)
             b = bias[l].contiguous() if bias[l] is not None else None
             yfull = y.gather().t
+            br.join()
             spmm(graph.fwd, M(yfull.view(yfull.size(0) * r, f)), hl, f, row_scale=graph.inv_cnt, bias=b, addend=hl,
                  relu=relu_flags[l])
             outs.append(hl)
             ws_list.append((w, bs, at, rt))
+        br.join()
         ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
         ctx.has_bias = [b is not None for b in bias]
         acts = [buf] if catout else [o.t for o in outs]

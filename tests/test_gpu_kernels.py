@@ -171,6 +171,43 @@ def test_distmult_forward_backward():
             assert rel_err(wc.grad, wr.grad) < TOL, (D, sig)
 
 
+@pytest.mark.parametrize("n", [645, 3000])
+def test_distmult_pose_sized_and_pair(n):
+    """Pose-sized decoder call (n = 645 drugs x D = 80, 400 k edges) and a larger table, against float64;
+    the fused pos/neg pair against two single calls (bit-identical)."""
+    from gripnet_b200 import ops
+    rs = np.random.RandomState(n)
+    d = _dev()
+    D, r, e = 80, 16, 400_000
+    z = torch.randn(n, D, dtype=torch.float64) * 0.3
+    w = torch.randn(r, D, dtype=torch.float64)
+    ei = torch.from_numpy(rs.randint(0, n, (2, e)))
+    ni = torch.from_numpy(rs.randint(0, n, (2, e)))
+    et = torch.from_numpy(np.sort(rs.randint(0, r, e)))
+    zr, wr = z.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    pos_ref = torch.sigmoid((zr[ei[0]] * zr[ei[1]] * wr[et]).sum(1))
+    neg_ref = torch.sigmoid((zr[ni[0]] * zr[ni[1]] * wr[et]).sum(1))
+    gp = torch.linspace(-1, 1, e, dtype=torch.float64)
+    gn = torch.linspace(0.5, -0.5, e, dtype=torch.float64)
+    ((pos_ref * gp).sum() + (neg_ref * gn).sum()).backward()
+    eid, nid, etd = ei.to(d), ni.to(d), et.to(d)
+    res = []
+    for pair in (False, True):
+        zc = z.float().to(d).requires_grad_(True)
+        wc = w.float().to(d).requires_grad_(True)
+        if pair:
+            pos, neg = ops.DistMultPair.apply(zc, wc, eid, nid, etd, True)
+        else:
+            pos, neg = ops.DistMult.apply(zc, wc, eid, etd, True), ops.DistMult.apply(zc, wc, nid, etd, True)
+        ((pos * gp.float().to(d)).sum() + (neg * gn.float().to(d)).sum()).backward()
+        torch.cuda.synchronize()
+        assert rel_err(pos, pos_ref) < TOL and rel_err(neg, neg_ref) < TOL
+        assert rel_err(zc.grad, zr.grad) < TOL and rel_err(wc.grad, wr.grad) < TOL
+        res.append((pos.detach(), neg.detach(), zc.grad.clone(), wc.grad.clone()))
+    for a, b in zip(*res):                       # same kernels, same summation order
+        assert torch.equal(a, b)
+
+
 def test_distmult_backward_deterministic_and_hub_rows():
     from gripnet_b200 import ops
     rs = np.random.RandomState(3)
