@@ -70,6 +70,9 @@ SIGNATURES = {
     "gn_lp_loss_bwd": (_INT, [_P, _I64, _P, _I64, _F, _P, _P, _P, _P]),
     "gn_nc_loss_fwd": (_INT, [_P, _I64, _I32, _P, _F, _P, _P, _SZ, _P]),
     "gn_nc_loss_bwd": (_INT, [_P, _I64, _I32, _P, _F, _P, _P, _P]),
+    "gn_negsample_table_bytes": (_SZ, [_I64]),
+    "gn_negsample_build": (_INT, [_P, _P, _I64, _I64, _P, _I32, _P, _SZ, _P]),
+    "gn_negsample_draw": (_INT, [_P, _SZ, _I64, _I64, _P, _I32, C.c_uint64, _P, _P, _P, _P]),
     "gn_peer_max_world": (_INT, []),
     "gn_peer_allgather": (_INT, [_P, _I32, _I32, _I64, _I64, _I64, _I32, _P, _P, _P, _P]),
 }

@@ -29,13 +29,82 @@ def remove_bidirection(edge_index, edge_type=None):
     return edge_index[:, keep] if edge_type is None else (edge_index[:, keep], edge_type[keep])
 
 
-def negative_sampling(pos_edge_index, num_nodes, generator=None):
-    """Uniform node pairs that are not positive edges, one per positive (utils.py:98-112).
+class NegativeSampler:
+    """One uniformly random NON-positive node pair per positive edge, drawn on the device
+    (``gn_negsample_build`` / ``gn_negsample_draw``; reference ``gripnet/utils.py:98-119``).
 
-    Same distribution as the reference (rejection sampling over ``num_nodes**2``
-    pair codes); the RNG stream is this function's own.  Returns int64 ``[2, E]`` on
-    the device of ``pos_edge_index``.
+    The positives are hashed once; every ``sample()`` is one kernel (counter-based Philox4x32-10, so the
+    result depends on ``(seed, epoch, edge)`` only) and advances the epoch counter, which lives in device
+    memory: a ``sample()`` captured in a CUDA graph yields new negatives on every replay.  With
+    ``range_list`` the typed rule applies (reject only the positives of the edge's own relation slice).
+    Same distribution as the reference; its own RNG stream (bit-exact restatement: ``oracle/negsample.py``).
     """
+
+    def __init__(self, pos_edge_index, num_nodes, range_list=None, seed=None):
+        from . import _lib
+        from .graph import _ptr, _stream, require_cuda
+        lib = _lib.load()
+        require_cuda(pos_edge_index, "pos_edge_index", torch.int64)
+        if pos_edge_index.dim() != 2 or pos_edge_index.size(0) != 2:
+            raise RuntimeError("pos_edge_index must have shape [2, E]")
+        dev = pos_edge_index.device
+        self.n_edges, self.n_nodes = int(pos_edge_index.size(1)), int(num_nodes)
+        ei = pos_edge_index.contiguous()
+        self.range_list, self.n_rel = None, 0
+        if range_list is not None:
+            rl = torch.as_tensor(range_list).to(torch.int64).cpu()
+            flat = rl.flatten().tolist()
+            n_rel = rl.size(0)
+            ok = rl.dim() == 2 and rl.size(1) == 2 and flat[0] == 0 and flat[-1] == self.n_edges and \
+                all(flat[2 * r + 1] == flat[2 * r + 2] for r in range(n_rel - 1)) and \
+                all(flat[2 * r] <= flat[2 * r + 1] for r in range(n_rel))
+            if not ok:
+                raise RuntimeError("range_list must partition [0, E) into ascending contiguous [start, end) slices")
+            self.range_list, self.n_rel = rl.to(dev).contiguous(), int(n_rel)
+        self.seed = int(torch.initial_seed() if seed is None else seed) & (2 ** 64 - 1)
+        self.table_bytes = int(lib.gn_negsample_table_bytes(self.n_edges))
+        self.table = torch.empty(max(self.table_bytes, 8), dtype=torch.uint8, device=dev)
+        self.state = torch.zeros(2, dtype=torch.int64, device=dev)          # [epoch, scratch]
+        _lib.check(lib.gn_negsample_build(_ptr(ei[0]) if self.n_edges else None, _ptr(ei[1]) if self.n_edges else None,
+                                          self.n_edges, self.n_nodes, _ptr(self.range_list), self.n_rel,
+                                          _ptr(self.table), self.table_bytes, _stream()), "gn_negsample_build")
+
+    def sample(self, out=None):
+        """int64 ``[2, E]`` negatives of the next epoch (into ``out`` when given)."""
+        from . import _lib
+        from .graph import _ptr, _stream
+        if out is None:
+            out = torch.empty((2, self.n_edges), dtype=torch.int64, device=self.table.device)
+        elif out.shape != (2, self.n_edges) or out.dtype != torch.int64 or not out.is_contiguous():
+            raise RuntimeError("out must be a contiguous int64 [2, E] tensor")
+        _lib.check(_lib.load().gn_negsample_draw(_ptr(self.table), self.table_bytes, self.n_edges, self.n_nodes,
+                                                 _ptr(self.range_list), self.n_rel, self.seed, _ptr(self.state),
+                                                 _ptr(out[0]) if self.n_edges else None,
+                                                 _ptr(out[1]) if self.n_edges else None, _stream()),
+                   "gn_negsample_draw")
+        return out
+
+    @property
+    def epoch(self):
+        return int(self.state[0].item())
+
+
+_samplers = {}
+
+
+def _sampler_for(pos_edge_index, num_nodes, range_list):
+    from .graph import _Cache
+    key = (_Cache.tkey(pos_edge_index), int(num_nodes),
+           None if range_list is None else tuple(torch.as_tensor(range_list).flatten().tolist()))
+    hit = _samplers.get(key)
+    if hit is None:
+        if len(_samplers) >= 8:
+            _samplers.pop(next(iter(_samplers)))
+        hit = _samplers[key] = (NegativeSampler(pos_edge_index, num_nodes, range_list), pos_edge_index)
+    return hit[0]
+
+
+def _host_negative_sampling(pos_edge_index, num_nodes, generator=None):
     rs = generator if generator is not None else np.random
     pos = pos_edge_index.detach().cpu().numpy().astype(np.int64)
     taken = np.unique(pos[0] * num_nodes + pos[1])
@@ -44,11 +113,26 @@ def negative_sampling(pos_edge_index, num_nodes, generator=None):
     while bad.any():
         code[bad] = rs.randint(0, num_nodes * num_nodes, size=int(bad.sum()))
         bad = np.isin(code, taken)
-    out = torch.from_numpy(np.stack([code // num_nodes, code % num_nodes]))
-    return out.to(pos_edge_index.device)
+    return torch.from_numpy(np.stack([code // num_nodes, code % num_nodes]))
+
+
+def negative_sampling(pos_edge_index, num_nodes, generator=None):
+    """Uniform node pairs that are not positive edges, one per positive (utils.py:98-112).
+
+    CUDA ``pos_edge_index``: sampled on the device (``NegativeSampler``, cached per edge tensor; successive
+    calls give successive epochs) — no device<->host round trip.  CPU tensors (data preparation): the
+    reference's numpy procedure with ``generator`` (a ``numpy.random.RandomState``) or the global numpy
+    RNG.  Same distribution as the reference either way; the RNG streams are this package's own.
+    """
+    if pos_edge_index.is_cuda:
+        return _sampler_for(pos_edge_index, num_nodes, None).sample()
+    return _host_negative_sampling(pos_edge_index, num_nodes, generator)
 
 
 def typed_negative_sampling(pos_edge_index, num_nodes, range_list, generator=None):
-    """Per-relation negative sampling (utils.py:115-119)."""
-    parts = [negative_sampling(pos_edge_index[:, int(s):int(e)], num_nodes, generator) for s, e in range_list]
+    """Per-relation negative sampling (utils.py:115-119): a draw is rejected only if it is a positive
+    pair of the SAME ``range_list`` slice."""
+    if pos_edge_index.is_cuda:
+        return _sampler_for(pos_edge_index, num_nodes, range_list).sample()
+    parts = [_host_negative_sampling(pos_edge_index[:, int(s):int(e)], num_nodes, generator) for s, e in range_list]
     return torch.cat(parts, dim=1)

@@ -247,6 +247,24 @@ int gn_nc_loss_fwd(const float* score, int64_t n, int32_t C, const int64_t* labe
 int gn_nc_loss_bwd(const float* score, int64_t n, int32_t C, const int64_t* label, float eps,
                    const float* grad_loss /*[1]*/, float* grad_score, void* stream);
 
+/* ---- K13: negative sampling on the device ---------------------------------- */
+/* Replaces gripnet/utils.py:98-112 (negative_sampling) and :115-119 (typed_negative_sampling): one
+ * uniformly random non-positive node pair per positive edge.  `range_list` ([n_rel,2] int64, ascending
+ * contiguous half-open slices, DEVICE) selects the typed rule (reject only pairs that are positive in
+ * the edge's own slice); NULL / n_rel == 0 rejects against all positives.
+ *   gn_negsample_build : hash the positives into `table` (gn_negsample_table_bytes(n_edges) bytes), once.
+ *   gn_negsample_draw  : one draw per edge into neg_src / neg_dst (int64 [n_edges]).  Draw `a` of edge e in
+ *                        epoch t = Philox4x32-10(counter (e_lo, e_hi, a, t), key seed); pair code =
+ *                        mulhi64(x0 | x1 << 32, N^2).  `state` = u64[2], zero-initialised: state[0] is the
+ *                        epoch, read by the kernel and advanced by it (CUDA-graph replays keep drawing new
+ *                        negatives), state[1] is scratch.  Bit-exact restatement: oracle/negsample.py. */
+size_t gn_negsample_table_bytes(int64_t n_edges);
+int gn_negsample_build(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_t n_nodes,
+                       const int64_t* range_list, int32_t n_rel, void* table, size_t table_bytes, void* stream);
+int gn_negsample_draw(const void* table, size_t table_bytes, int64_t n_edges, int64_t n_nodes,
+                      const int64_t* range_list, int32_t n_rel, uint64_t seed, uint64_t* state,
+                      int64_t* neg_src, int64_t* neg_dst, void* stream);
+
 /* ---- K12: slot all-gather over NVLink peer memory (multi-GPU exchange step) ------------------ */
 /* New design (the reference is single-device).  Every rank of the node maps one
  * symmetric arena of identical layout; `arena_base` (HOST array, `world` entries) holds every rank's
