@@ -25,6 +25,12 @@ class GnCsr(C.Structure):
     ]
 
 
+class GnAdamTensor(C.Structure):
+    """Mirror of ``gn_adam_tensor`` (include/gripnet_b200.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_int64)]
+
+
 _P, _I32, _I64, _F, _SZ, _INT = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_int
 _CSR = C.POINTER(GnCsr)
 
@@ -73,6 +79,13 @@ SIGNATURES = {
     "gn_negsample_table_bytes": (_SZ, [_I64]),
     "gn_negsample_build": (_INT, [_P, _P, _I64, _I64, _P, _I32, _P, _SZ, _P]),
     "gn_negsample_draw": (_INT, [_P, _SZ, _I64, _I64, _P, _I32, C.c_uint64, _P, _P, _P, _P]),
+    "gn_adam_max_tensors_per_launch": (_INT, []),
+    "gn_adam_step": (_INT, [_P, _I32, _F, _F, _F, _F, _F, _P, _P]),
+    "gn_lp_metrics_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
+    "gn_lp_metrics": (_INT, [_P, _I64, _P, _I64, _P, _P, _I32, _P, _P, _SZ, _P]),
+    "gn_argmax_rows": (_INT, [_P, _I64, _I64, _I32, _P, _P]),
+    "gn_nc_metrics_workspace_bytes": (_SZ, [_I32]),
+    "gn_nc_metrics": (_INT, [_P, _P, _I64, _I32, _P, _P, _SZ, _P]),
     "gn_peer_max_world": (_INT, []),
     "gn_peer_allgather": (_INT, [_P, _I32, _I32, _I64, _I64, _I64, _I32, _P, _P, _P, _P]),
 }

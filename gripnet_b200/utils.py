@@ -10,6 +10,24 @@ import torch
 EPS = 1e-13                                    # utils.py:10
 
 
+def auprc_auroc_ap(target_tensor, score_tensor):
+    """utils.py:28-35 — on the device for CUDA tensors (``metrics.lp_metrics``: one sort, no sklearn)."""
+    from . import metrics
+    return metrics.auprc_auroc_ap(target_tensor, score_tensor)
+
+
+def micro_macro(target_tensor, score_tensor):
+    """utils.py:38-46 — micro / macro F1 of class predictions, on the device."""
+    from . import metrics
+    return metrics.micro_macro(target_tensor, score_tensor)
+
+
+def acc(target_tensor, score_tensor):
+    """utils.py:49-52 — accuracy of class predictions, on the device."""
+    from . import metrics
+    return metrics.acc(target_tensor, score_tensor)
+
+
 def get_range_list(edge_list, is_node=False):
     """Half-open ``[start, end)`` index ranges of consecutive blocks (utils.py:141-148)."""
     axis = 0 if is_node else 1
@@ -82,7 +100,8 @@ class NegativeSampler:
                                                  _ptr(out[0]) if self.n_edges else None,
                                                  _ptr(out[1]) if self.n_edges else None, _stream()),
                    "gn_negsample_draw")
-        return out
+        torch.autograd.graph.increment_version(out)      # written behind torch's back: structures cached per
+        return out                                       # (tensor, version) must be rebuilt for the new draw
 
     @property
     def epoch(self):

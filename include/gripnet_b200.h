@@ -265,6 +265,49 @@ int gn_negsample_draw(const void* table, size_t table_bytes, int64_t n_edges, in
                       const int64_t* range_list, int32_t n_rel, uint64_t seed, uint64_t* state,
                       int64_t* neg_src, int64_t* neg_dst, void* stream);
 
+/* ---- K14: fused multi-tensor Adam -------------------------------------- */
+/* Replaces torch.optim.Adam(model.parameters(), lr).step() of the training scripts
+ * (GripNet-pose.py:104,146; GripNet-aminer.py:113,135; amsgrad = False):
+ *   g' = g + weight_decay * p;  m += (g' - m)(1 - beta1);  v = v beta2 + (1 - beta2) g'^2;
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps),   t = step[0] + 1.
+ * `tensors` is a HOST array (the descriptors travel in the kernel-parameter block, up to
+ * gn_adam_max_tensors_per_launch() per launch); all pointers inside are DEVICE pointers to contiguous
+ * fp32 arrays of n elements.  `step` is a DEVICE u64, zero-initialised by the caller, read by the
+ * kernels and advanced by one at the end of the call: replays of a captured CUDA graph are successive
+ * optimiser steps. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+} gn_adam_tensor;
+int gn_adam_max_tensors_per_launch(void);
+int gn_adam_step(const gn_adam_tensor* tensors /*host*/, int32_t n_tensors, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, uint64_t* step, void* stream);
+
+/* ---- K15: evaluation metrics on the device ------------------------------ */
+/* Per-relation AUPRC / AUROC / AP of a link-prediction epoch.  Replaces the host loop of
+ * GripNet-pose.py:148-164 and :188-199 around gripnet/utils.py:28-35 (sklearn roc_auc_score,
+ * average_precision_score, auc(precision_recall_curve)).  Relation r scores the positives
+ * pos_score[pos_range[r,0] : pos_range[r,1]] against the negatives neg_score[neg_range[r,0] :
+ * neg_range[r,1]] (neg_range == NULL: the same slices, as the reference does).  Ranges are DEVICE int64
+ * [n_rel,2], ascending and non-overlapping.  record: DEVICE double [3, n_rel], rows = auprc, auroc, ap
+ * (the reference's `record` layout, GripNet-pose.py:148); NaN where the metric is undefined (a relation
+ * without positives; AUROC also without negatives).  Tied scores form one threshold, as in sklearn. */
+size_t gn_lp_metrics_workspace_bytes(int64_t n_pos, int64_t n_neg, int32_t n_rel);
+int gn_lp_metrics(const float* pos_score, int64_t n_pos, const float* neg_score, int64_t n_neg,
+                  const int64_t* pos_range, const int64_t* neg_range, int32_t n_rel, double* record,
+                  void* ws, size_t ws_bytes, void* stream);
+/* out[i] = index of the first maximum of row i (torch.argmax(score, dim=1), GripNet-aminer.py:131) */
+int gn_argmax_rows(const float* x, int64_t ldx, int64_t n, int32_t C, int64_t* out, void* stream);
+/* out (DEVICE double[3]) = {micro-F1, macro-F1, accuracy} of integer class predictions
+ * (gripnet/utils.py:38-52: sklearn f1_score micro / macro over the classes present, accuracy_score).
+ * NaN if a label lies outside [0, C). */
+size_t gn_nc_metrics_workspace_bytes(int32_t C);
+int gn_nc_metrics(const int64_t* target, const int64_t* pred, int64_t n, int32_t C, double* out,
+                  void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K12: slot all-gather over NVLink peer memory (multi-GPU exchange step) ------------------ */
 /* New design (the reference is single-device).  Every rank of the node maps one
  * symmetric arena of identical layout; `arena_base` (HOST array, `world` entries) holds every rank's
