@@ -80,7 +80,7 @@ SIGNATURES = {
     "gn_negsample_build": (_INT, [_P, _P, _I64, _I64, _P, _I32, _P, _SZ, _P]),
     "gn_negsample_draw": (_INT, [_P, _SZ, _I64, _I64, _P, _I32, C.c_uint64, _P, _P, _P, _P]),
     "gn_adam_max_tensors_per_launch": (_INT, []),
-    "gn_adam_step": (_INT, [_P, _I32, _F, _F, _F, _F, _F, _P, _P]),
+    "gn_adam_step": (_INT, [_P, _I32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     "gn_lp_metrics_workspace_bytes": (_SZ, [_I64, _I64, _I32]),
     "gn_lp_metrics": (_INT, [_P, _I64, _P, _I64, _P, _P, _I32, _P, _P, _SZ, _P]),
     "gn_argmax_rows": (_INT, [_P, _I64, _I64, _I32, _P, _P]),

@@ -11,8 +11,9 @@
 //   m  = m + (g' - m) * (1 - beta1)     (lerp)
 //   v  = v * beta2 + (1 - beta2) * g' * g'
 //   p  = p - (lr / (1 - beta1^t)) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
-// with the bias corrections evaluated in double (as torch does on the host) and everything
-// elementwise in fp32.  HBM-bound: 28 B per element (p, m, v read+write, g read).
+// with the hyper-parameters taken as doubles: the bias corrections and (1 - beta) are evaluated in double and
+// only then cast to fp32 (as torch does on the host; 1 - float(0.999) would be off by 1.3e-5 relative), and
+// everything elementwise in fp32.  HBM-bound: 28 B per element (p, m, v read+write, g read).
 #include "common.cuh"
 
 namespace gn {
@@ -33,14 +34,15 @@ struct AdamBatch {
 };
 
 struct AdamHyper {
-  float lr, beta1, beta2, eps, weight_decay;
+  double lr, beta1, beta2;                                   // bias corrections are evaluated in double
+  float beta2f, one_minus_beta1, one_minus_beta2, eps, weight_decay;   // float(double expression), as torch casts them
 };
 
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamHyper& h, float step_size,
                                             float bc2_sqrt) {
   if (h.weight_decay != 0.f) g = __fmaf_rn(h.weight_decay, p, g);
-  m = m + (g - m) * (1.f - h.beta1);
-  v = v * h.beta2 + (1.f - h.beta2) * g * g;
+  m = m + (g - m) * h.one_minus_beta1;
+  v = v * h.beta2f + h.one_minus_beta2 * g * g;
   const float denom = sqrtf(v) / bc2_sqrt + h.eps;
   p = p - step_size * (m / denom);
 }
@@ -51,9 +53,9 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(const AdamBatch b, c
   __shared__ int s_slot;
   if (threadIdx.x == 0) {
     const double t = double(step[0] + 1);
-    const double bc1 = 1.0 - pow(double(h.beta1), t);
-    const double bc2 = 1.0 - pow(double(h.beta2), t);
-    s_step_size = float(double(h.lr) / bc1);
+    const double bc1 = 1.0 - pow(h.beta1, t);
+    const double bc2 = 1.0 - pow(h.beta2, t);
+    s_step_size = float(h.lr / bc1);
     s_bc2_sqrt = float(sqrt(bc2));
     int s = 0;
     while (s + 1 < b.n_tensors && int(blockIdx.x) >= b.block_first[s + 1]) ++s;
@@ -108,13 +110,14 @@ extern "C" {
 
 int gn_adam_max_tensors_per_launch(void) { return kAdamSlots; }
 
-int gn_adam_step(const gn_adam_tensor* tensors, int32_t n_tensors, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, uint64_t* step, void* stream) {
+int gn_adam_step(const gn_adam_tensor* tensors, int32_t n_tensors, double lr, double beta1, double beta2, double eps,
+                 double weight_decay, uint64_t* step, void* stream) {
   if (n_tensors < 0 || (n_tensors > 0 && tensors == nullptr) || step == nullptr) return GN_ERR_ARG;
-  if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f) || !(lr >= 0.f))
+  if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0) || !(lr >= 0.0))
     return GN_ERR_ARG;
   cudaStream_t st = as_stream(stream);
-  const AdamHyper h{lr, beta1, beta2, eps, weight_decay};
+  const AdamHyper h{lr, beta1, beta2, float(beta2), float(1.0 - beta1), float(1.0 - beta2), float(eps),
+                    float(weight_decay)};
   int32_t i = 0;
   while (i < n_tensors) {
     AdamBatch b;

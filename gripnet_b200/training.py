@@ -15,8 +15,26 @@ from .optim import Adam
 from .utils import NegativeSampler
 
 
+class _EagerStep:
+    """The same epoch launched kernel by kernel (profilers cannot follow a graph capture)."""
+
+    def __init__(self, fn, params, post):
+        self.fn, self.params, self.post, self.launches_per_replay = fn, params, post, 0
+
+    def replay(self):
+        from . import _lib
+        for p in self.params:
+            p.grad = None
+        before = _lib.launch_count()
+        self.outputs = self.fn()
+        self.outputs[0].backward()
+        self.post()
+        self.launches_per_replay = _lib.launch_count() - before
+        return self.outputs
+
+
 class _Trainer:
-    def _capture(self, fn, model, lr, warmup, post_extra=None):
+    def _capture(self, fn, model, lr, warmup, post_extra=None, eager=False):
         params = [p for p in model.parameters() if p.requires_grad]
         self.optimizer = Adam(params, lr=lr)
         start = [p.detach().clone() for p in params]
@@ -26,6 +44,10 @@ class _Trainer:
             if post_extra is not None:
                 post_extra()
 
+        if eager:
+            self.step = _EagerStep(fn, params, post)
+            self.epoch = 0
+            return
         self.step = CapturedStep(fn, params, warmup=warmup, post_backward=post)
         # warm-up and capture ran real optimiser steps: rewind parameters, moments and the step counter
         with torch.no_grad():
@@ -46,7 +68,8 @@ class _Trainer:
 class PoseTrainer(_Trainer):
     """``model``: ``pipelines.PoseModel``; ``data``: its device dict (``gg_edge_index`` … ``dd_range_list``)."""
 
-    def __init__(self, model, data, lr=0.01, seed=1111, typed_negatives=False, with_metrics=True, warmup=3):
+    def __init__(self, model, data, lr=0.01, seed=1111, typed_negatives=False, with_metrics=True, warmup=3,
+                 eager=False):
         ei = data["dd_edge_index"]
         n_d = int(data["n_d"])
         self.range_list = data["dd_range_list"].to(ei.device).contiguous()
@@ -69,7 +92,7 @@ class PoseTrainer(_Trainer):
                 _, _, pos_score, neg_score = outs["o"]
                 metrics.lp_metrics(pos_score, neg_score, self.range_list, out=self.record)
 
-        self._capture(fn, model, lr, warmup, post_extra)
+        self._capture(fn, model, lr, warmup, post_extra, eager)
         self.sampler.state.zero_()                         # epoch 0 draws the sampler's first negatives
 
     def train_epoch(self):
@@ -83,7 +106,7 @@ class PoseTrainer(_Trainer):
 class NodeTrainer(_Trainer):
     """``model(data) -> (loss, z, score)`` (``pipelines.AminerModel`` / ``FreebaseDModel`` / ``ChainModel``)."""
 
-    def __init__(self, model, data, n_class, lr=0.01, with_metrics=True, warmup=3):
+    def __init__(self, model, data, n_class, lr=0.01, with_metrics=True, warmup=3, eager=False):
         dev = data["train_node_class"].device
         self.f1 = torch.full((3,), float("nan"), dtype=torch.float64, device=dev) if with_metrics else None
         outs = {}
@@ -98,7 +121,7 @@ class NodeTrainer(_Trainer):
                 self.pred = metrics.argmax_rows(score)
                 metrics.nc_metrics(data["train_node_class"], self.pred, n_class, out=self.f1)
 
-        self._capture(fn, model, lr, warmup, post_extra)
+        self._capture(fn, model, lr, warmup, post_extra, eager)
 
     def train_epoch(self):
         self.loss, self.z, self.score = self.step.replay()

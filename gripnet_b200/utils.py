@@ -155,3 +155,87 @@ def typed_negative_sampling(pos_edge_index, num_nodes, range_list, generator=Non
         return _sampler_for(pos_edge_index, num_nodes, range_list).sample()
     parts = [_host_negative_sampling(pos_edge_index[:, int(s):int(e)], num_nodes, generator) for s, e in range_list]
     return torch.cat(parts, dim=1)
+
+
+# ---- host-side data preparation (gripnet/utils.py:13-25, :55-95, :151-272): not kernels; present so a script
+#      written against ``gripnet.utils`` imports and prepares its splits unchanged ---------------------------
+def normalize(input):
+    """Rows scaled to unit L2 norm (utils.py:13-15)."""
+    return input / input.pow(2).sum(dim=1, keepdim=True).sqrt()
+
+
+def sparse_id(n):
+    """``n x n`` sparse identity (utils.py:18-25; the scripts' one-hot node features, which ``homoGraph``
+    ignores when ``start_graph=True``, layers.py:261-262)."""
+    i = torch.arange(n, dtype=torch.int64)
+    return torch.sparse_coo_tensor(torch.stack([i, i]), torch.ones(n), (n, n), check_invariants=False)
+
+
+def load_graph(pt_file_path="./sample_graph.pt"):
+    """utils.py:55-79 — opens the pickled ``torch_geometric.data.Data`` without PyG (``data.load``)."""
+    from . import data
+    return data.load(pt_file_path)
+
+
+def load_node_idx_to_id_dict(pkl_file_path="./data/pose-1/map.pkl"):
+    """utils.py:83-95."""
+    import pickle
+    with open(pkl_file_path, "rb") as f:
+        return pickle.load(f)
+
+
+def _bernoulli_split(n, p):
+    keep = np.random.binomial(1, p, n).astype(bool)
+    return np.flatnonzero(keep), np.flatnonzero(~keep)
+
+
+def process_edge(raw_edges):
+    """90/10 edge split on one direction, both halves mirrored back (utils.py:151-165)."""
+    one_way = remove_bidirection(raw_edges, None)
+    tr, te = _bernoulli_split(one_way.shape[1], 0.9)
+    return to_bidirection(one_way[:, tr], None), to_bidirection(one_way[:, te], None)
+
+
+def process_edge_multirelational(raw_edge_list, p=0.9):
+    """Per-relation Bernoulli(p) split, mirrored, concatenated relation-major (utils.py:168-198): returns
+    ``train_idx, train_et, train_range, test_idx, test_et, test_range``."""
+    parts = {"train": [], "test": []}
+    for idx in raw_edge_list:
+        tr, te = _bernoulli_split(idx.shape[1], p)
+        parts["train"].append(to_bidirection(idx[:, tr]))
+        parts["test"].append(to_bidirection(idx[:, te]))
+    out = []
+    for name in ("train", "test"):
+        lists = parts[name]
+        et = torch.cat([torch.full((e.shape[1],), r, dtype=torch.long) for r, e in enumerate(lists)])
+        out += [torch.cat(lists, dim=1), et, get_range_list(lists)]
+    return tuple(out)
+
+
+def process_node(raw_nodes, p=0.9):
+    """Bernoulli(0.9) node split (utils.py:201-209; ``p`` is accepted and ignored there too)."""
+    tr, te = _bernoulli_split(len(raw_nodes), 0.9)
+    return raw_nodes[tr], raw_nodes[te]
+
+
+def process_node_multilabel(raw_nodes_list):
+    """Per-class node split (utils.py:212-247): ``train_idx, train_class, train_range, test_idx, test_class,
+    test_range``."""
+    splits = [process_node(idx) for idx in raw_nodes_list]
+    out = []
+    for k in (0, 1):
+        lists = [s[k] for s in splits]
+        cls = torch.cat([torch.full((len(v),), c, dtype=torch.long) for c, v in enumerate(lists)])
+        out += [torch.cat(lists), cls, get_range_list(lists, is_node=True)]
+    return tuple(out)
+
+
+def process_data_multiclass(torch_tensor, n_class):
+    """``[node ids; labels]`` regrouped class-major (utils.py:250-262): ``node_idx, node_class, range`` with
+    ``range`` a list of ``[start, end]`` pairs."""
+    nodes, labels = torch_tensor[0], torch_tensor[1]
+    groups = [nodes[labels == c] for c in range(n_class)]
+    sizes = [int(g.shape[0]) for g in groups]
+    bounds = np.cumsum([0] + sizes).tolist()
+    cls = torch.cat([torch.full((m,), c, dtype=torch.int64) for c, m in enumerate(sizes)])
+    return torch.cat(groups), cls, [[bounds[c], bounds[c + 1]] for c in range(n_class)]

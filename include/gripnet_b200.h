@@ -272,7 +272,8 @@ int gn_negsample_draw(const void* table, size_t table_bytes, int64_t n_edges, in
  *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps),   t = step[0] + 1.
  * `tensors` is a HOST array (the descriptors travel in the kernel-parameter block, up to
  * gn_adam_max_tensors_per_launch() per launch); all pointers inside are DEVICE pointers to contiguous
- * fp32 arrays of n elements.  `step` is a DEVICE u64, zero-initialised by the caller, read by the
+ * fp32 arrays of n elements.  Hyper-parameters are doubles (torch evaluates 1 - beta and the bias corrections
+ * in double before casting).  `step` is a DEVICE u64, zero-initialised by the caller, read by the
  * kernels and advanced by one at the end of the call: replays of a captured CUDA graph are successive
  * optimiser steps. */
 typedef struct {
@@ -283,8 +284,8 @@ typedef struct {
   int64_t n;
 } gn_adam_tensor;
 int gn_adam_max_tensors_per_launch(void);
-int gn_adam_step(const gn_adam_tensor* tensors /*host*/, int32_t n_tensors, float lr, float beta1, float beta2,
-                 float eps, float weight_decay, uint64_t* step, void* stream);
+int gn_adam_step(const gn_adam_tensor* tensors /*host*/, int32_t n_tensors, double lr, double beta1, double beta2,
+                 double eps, double weight_decay, uint64_t* step, void* stream);
 
 /* ---- K15: evaluation metrics on the device ------------------------------ */
 /* Per-relation AUPRC / AUROC / AP of a link-prediction epoch.  Replaces the host loop of
