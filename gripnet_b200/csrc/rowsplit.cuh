@@ -79,8 +79,8 @@ struct ChunkInfo {
   int chunk, row, beg, end, first_chunk, n_chunks_of_row;
 };
 
-__device__ __forceinline__ bool chunk_info(const gn_csr& csr, ChunkInfo& ci) {
-  const int warp = int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5);
+// chunk `warp` of the work list (false when it lies beyond the list)
+__device__ __forceinline__ bool chunk_info_at(const gn_csr& csr, int warp, ChunkInfo& ci) {
   if (warp >= csr.n_chunks) return false;
   if (warp >= __ldg(csr.chunk_ptr + csr.n_rows)) return false;
   ci.chunk = warp;
@@ -93,10 +93,55 @@ __device__ __forceinline__ bool chunk_info(const gn_csr& csr, ChunkInfo& ci) {
   return true;
 }
 
+// one warp per chunk, chunk = global warp index
+__device__ __forceinline__ bool chunk_info(const gn_csr& csr, ChunkInfo& ci) {
+  return chunk_info_at(csr, int((int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5), ci);
+}
+
+// Sum the k partial rows of a split row in chunk order (slot s takes chunks s, s+EPI, ...; the slots are
+// combined afterwards in the fixed shuffle order).  Rows of a few hundred chunks (relation rows of the
+// decoder backward, hub rows of power-law graphs) make this the tail of the kernel, so DEPTH partial rows x
+// NV vectors are in flight per step instead of one dependent load at a time; the order of the additions is
+// that of a plain loop.  DEPTH 1 costs no registers beyond the accumulators it replaces.
+template <int LPE, int VEC, int NV, int DEPTH>
+__device__ __forceinline__ void sum_partials(const float* __restrict__ rows, int k, int width, int slot, int fl,
+                                          Vec<VEC> (&s)[NV]) {
+  constexpr int EPI = 32 / LPE;
+  constexpr int kTailDepth = DEPTH;
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[v].v[i] = 0.f;
+  for (int j0 = slot; j0 < k; j0 += kTailDepth * EPI) {
+    Vec<VEC> p[kTailDepth][NV];
+#pragma unroll
+    for (int u = 0; u < kTailDepth; ++u) {
+      const int j = j0 + u * EPI;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int f = (v * LPE + fl) * VEC;
+        if (j < k && f < width) p[u][v] = load_vec_cg<VEC>(rows + int64_t(j) * width + f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTailDepth; ++u) {
+      const int j = j0 + u * EPI;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int f = (v * LPE + fl) * VEC;
+        if (j < k && f < width) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) s[v].v[i] += p[u][v].v[i];
+        }
+      }
+    }
+  }
+}
+
 // Finish a row.  `acc[NV]` holds this warp's slot-reduced sums (valid on slot 0);
 // `width` = number of floats per row; feature lane `fl` owns floats
 // [ (v*LPE + fl)*VEC , +VEC ) for v < NV.  `emit(v, f, vec)` writes the result.
-template <int LPE, int VEC, int NV, typename Emit>
+template <int LPE, int VEC, int NV, int TAIL_DEPTH = 1, typename Emit>
 __device__ __forceinline__ void finish_row(const gn_csr& csr, const ChunkInfo& ci, Vec<VEC> (&acc)[NV], int width,
                                            float* __restrict__ partial, Emit emit) {
   constexpr int EPI = 32 / LPE;
@@ -130,21 +175,13 @@ __device__ __forceinline__ void finish_row(const gn_csr& csr, const ChunkInfo& c
   last = __shfl_sync(kFull, last, 0);
   if (!last) return;
   __threadfence();
+  Vec<VEC> s[NV];
+  sum_partials<LPE, VEC, NV, TAIL_DEPTH>(partial + pbase * width, ci.n_chunks_of_row, width, slot, fl, s);
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int f = (v * LPE + fl) * VEC;
-    Vec<VEC> s;
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s.v[i] = 0.f;
-    if (f < width) {
-      for (int j = slot; j < ci.n_chunks_of_row; j += EPI) {
-        const Vec<VEC> p = load_vec_cg<VEC>(partial + (pbase + j) * width + f);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) s.v[i] += p.v[i];
-      }
-    }
-    reduce_slots<LPE, VEC>(s);
-    if (slot == 0 && f < width) emit(v, f, s);
+    reduce_slots<LPE, VEC>(s[v]);
+    if (slot == 0 && f < width) emit(v, f, s[v]);
   }
   if (lane == 0) csr.row_counter[ci.row] = 0;  // every warp of this row has arrived: safe to re-arm
 }

@@ -542,9 +542,30 @@ def _distmult_check(z, weight, edge_index, edge_type):
     return z, w, edge_index.contiguous(), edge_type.contiguous()
 
 
+# decoder path: "auto" keeps the embedding table in shared memory whenever it fits one SM (the task supervertex
+# of every pose dataset: 645 x 80 floats), "global" forces the global-memory gather kernels
+DECODER_PATH = os.environ.get("GRIPNET_B200_DECODER", "auto")
+
+
+def _z_resident(z):
+    if DECODER_PATH == "global":
+        return False
+    n, d = z.size(0), z.size(1)
+    ok = bool(_lib.load().gn_distmult_resident_ok(n, d, z.stride(0) if n > 1 else d)) and z.data_ptr() % 16 == 0
+    if DECODER_PATH == "resident" and not ok:
+        raise RuntimeError("GRIPNET_B200_DECODER=resident: the embedding table does not fit shared memory")
+    return ok
+
+
 def _distmult_fwd(z, w, ei, et, sigmoid):
     e = ei.size(1)
     out = torch.empty(e, dtype=torch.float32, device=z.device)
+    if e and _z_resident(z) and w.data_ptr() % 16 == 0:
+        _lib.check(_lib.load().gn_distmult_fwd_resident(z.data_ptr(), z.stride(0) if z.size(0) > 1 else z.size(1),
+                                                        z.size(0), z.size(1), w.data_ptr(), _ptr(ei[0]), _ptr(ei[1]),
+                                                        _ptr(et), e, int(sigmoid), _ptr(out), _stream()),
+                   "gn_distmult_fwd_resident")
+        return out
     _lib.check(_lib.load().gn_distmult_fwd(z.data_ptr(), z.stride(0) if z.size(0) > 1 else z.size(1), z.size(1),
                                            w.data_ptr(), _ptr(ei[0]) if e else None, _ptr(ei[1]) if e else None,
                                            _ptr(et) if e else None, e, int(sigmoid), _ptr(out), _stream()),
@@ -567,6 +588,12 @@ def _distmult_dz(key_tensors, coef, z, w):
     es = edge_struct(key_tensors[0], key_tensors[1], n, r)
     dz = torch.empty((n, d), dtype=torch.float32, device=z.device)
     part = es.node.partial(d)
+    if _z_resident(z) and w.data_ptr() % 16 == 0:
+        _lib.check(_lib.load().gn_distmult_bwd_z_resident(
+            es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid), _ptr(coef), z.data_ptr(),
+            z.stride(0) if n > 1 else d, d, w.data_ptr(), dz.data_ptr(), d, _ptr(part), _stream()),
+            "gn_distmult_bwd_z_resident")
+        return dz
     _lib.check(_lib.load().gn_distmult_bwd_z(es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid),
                                              _ptr(coef), z.data_ptr(), z.stride(0) if n > 1 else d, d, w.data_ptr(),
                                              dz.data_ptr(), d, _ptr(part), _stream()), "gn_distmult_bwd_z")
@@ -580,6 +607,11 @@ def _distmult_dw(dw, edge_type_key, ei, coef, z, alt=False):
     n, d, r, e = z.size(0), z.size(1), dw.size(0), ei.size(1)
     rs = rel_struct(edge_type_key, r)
     part = rs.csr.partial(d)
+    if e and _z_resident(z):
+        _lib.check(_lib.load().gn_distmult_bwd_w_resident(
+            rs.csr.alt_ref() if alt else rs.csr.ref, _ptr(rs.perm), _ptr(ei[0]), _ptr(ei[1]), _ptr(coef), z.data_ptr(),
+            z.stride(0) if n > 1 else d, n, d, dw.data_ptr(), _ptr(part), _stream()), "gn_distmult_bwd_w_resident")
+        return
     _lib.check(_lib.load().gn_distmult_bwd_w(rs.csr.alt_ref() if alt else rs.csr.ref, _ptr(rs.perm), _ptr(ei[0]) if e else None,
                                              _ptr(ei[1]) if e else None, _ptr(coef), z.data_ptr(),
                                              z.stride(0) if n > 1 else d, d, dw.data_ptr(), _ptr(part), _stream()),

@@ -207,6 +207,23 @@ int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64
                       const int64_t* dst, const float* coef, const float* z, int64_t ldz,
                       int32_t D, float* dw, float* partial, void* stream);
 
+/* K9/K10 with the embedding table RESIDENT in shared memory: the decoder scores edges inside the task
+ * supervertex, whose table is small (645 x 80 floats = 206 KB on every pose dataset) — when
+ * n_nodes * D * 4 <= 227 KB (gn_distmult_resident_ok) one persistent CTA per SM copies z into shared memory once
+ * and every row gather of the three kernels is a conflict-free shared-memory read instead of an L1 lookup.
+ * Same arguments, results and determinism as the calls above (the forward also takes n_nodes, the weight
+ * gradient n_nodes); requires D % 4 == 0, ldz % 4 == 0 and 16-byte aligned z / w / outputs. */
+int gn_distmult_resident_ok(int64_t n_nodes, int32_t D, int64_t ldz);
+int gn_distmult_fwd_resident(const float* z, int64_t ldz, int32_t n_nodes, int32_t D, const float* w,
+                             const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges,
+                             int sigmoid, float* out, void* stream);
+int gn_distmult_bwd_z_resident(const gn_csr* node_csr, const int32_t* ent_other, const int32_t* ent_rel,
+                               const int32_t* ent_eid, const float* coef, const float* z, int64_t ldz, int32_t D,
+                               const float* w, float* dz, int64_t lddz, float* partial, void* stream);
+int gn_distmult_bwd_w_resident(const gn_csr* rel_csr, const int32_t* rel_eid, const int64_t* src,
+                               const int64_t* dst, const float* coef, const float* z, int64_t ldz, int32_t n_nodes,
+                               int32_t D, float* dw, float* partial, void* stream);
+
 /* ---- K11: multi-class decoder pieces  ------------------------------------ */
 /* row softmax over C columns (gripnet/decoder.py:43) and its backward */
 int gn_softmax_fwd(const float* logits, int64_t n, int32_t C, float* out, void* stream);

@@ -20,7 +20,16 @@ def timeit(fn, reps=50):
     for _ in range(reps): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps * 1e3
-print("ZS env", os.environ.get("GRIPNET_B200_ZS"))
+print("decoder path", ops.DECODER_PATH)
 print("fwd us", timeit(lambda: ops._distmult_fwd(z, w, ei, et, True)))
 print("dz  us", timeit(lambda: ops._distmult_dz((ei, et), coef, z, w)))
 print("dw  us", timeit(lambda: ops._distmult_dw(dw, et, ei, coef, z)))
+if ops.DECODER_PATH == "auto":
+    # the two families agree to fp32 round-off
+    ops.DECODER_PATH = "global"
+    o2 = ops._distmult_fwd(z, w, ei, et, True); dz2 = ops._distmult_dz((ei, et), coef, z, w)
+    dw2 = torch.empty_like(w); ops._distmult_dw(dw2, et, ei, coef, z)
+    ops.DECODER_PATH = "auto"
+    dz1 = ops._distmult_dz((ei, et), coef, z, w); ops._distmult_dw(dw, et, ei, coef, z)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    print("resident vs global rel diff: fwd %.2e dz %.2e dw %.2e" % (rel(out, o2), rel(dz1, dz2), rel(dw, dw2)))

@@ -147,11 +147,21 @@ def test_sgemm_epilogue_batch_and_gather():
     assert rel_err(dX, np.einsum("mrn,rkn->mk", Y.cpu().numpy().astype(np.float64), W)) < TOL
 
 
-def test_distmult_forward_backward():
+@pytest.fixture(params=["auto", "global"])
+def decoder_path(request, monkeypatch):
+    """Both decoder kernel families: "auto" = table resident in shared memory where it fits (decoder_resident.cu),
+    "global" = the global-memory gather kernels (decoder.cu) for every shape."""
+    from gripnet_b200 import ops
+    monkeypatch.setattr(ops, "DECODER_PATH", request.param)
+    return request.param
+
+
+def test_distmult_forward_backward(decoder_path):
     from gripnet_b200 import ops
     rs = np.random.RandomState(2)
     d = _dev()
-    for D, n, r, e in [(80, 64, 5, 3000), (20, 30, 3, 100), (7, 10, 2, 50), (160, 40, 4, 500), (288, 20, 3, 200)]:
+    for D, n, r, e in [(80, 64, 5, 3000), (20, 30, 3, 100), (7, 10, 2, 50), (160, 40, 4, 500), (288, 20, 3, 200),
+                       (128, 100, 6, 5000), (48, 7, 1, 33), (96, 300, 40, 20000)]:
         z = torch.randn(n, D, dtype=torch.float64)
         w = torch.randn(r, D, dtype=torch.float64)
         ei = torch.from_numpy(rs.randint(0, n, (2, e)))
@@ -172,7 +182,7 @@ def test_distmult_forward_backward():
 
 
 @pytest.mark.parametrize("n", [645, 3000])
-def test_distmult_pose_sized_and_pair(n):
+def test_distmult_pose_sized_and_pair(n, decoder_path):
     """Pose-sized decoder call (n = 645 drugs x D = 80, 400 k edges) and a larger table, against float64;
     the fused pos/neg pair against two single calls (bit-identical)."""
     from gripnet_b200 import ops
@@ -208,7 +218,7 @@ def test_distmult_pose_sized_and_pair(n):
         assert torch.equal(a, b)
 
 
-def test_distmult_backward_deterministic_and_hub_rows():
+def test_distmult_backward_deterministic_and_hub_rows(decoder_path):
     from gripnet_b200 import ops
     rs = np.random.RandomState(3)
     d = _dev()
