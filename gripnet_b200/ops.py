@@ -542,9 +542,12 @@ def _distmult_check(z, weight, edge_index, edge_type):
     return z, w, edge_index.contiguous(), edge_type.contiguous()
 
 
-# decoder path: "auto" keeps the embedding table in shared memory whenever it fits one SM (the task supervertex
-# of every pose dataset: 645 x 80 floats), "global" forces the global-memory gather kernels
-DECODER_PATH = os.environ.get("GRIPNET_B200_DECODER", "auto")
+# decoder path: "global" = the global-memory gather kernels (decoder.cu); "auto" keeps the embedding table in
+# shared memory whenever it fits one SM (decoder_resident.cu; the task supervertex of every pose dataset is
+# 645 x 80 floats), "resident" insists on it.  Measured on B200 (profiles/r01_v7_*): the resident family is
+# NOT faster — the decoder is bound by the latency of its index / coefficient streams at the occupancy one
+# 206 KB CTA per SM allows, not by the L1 row gathers — so the default stays "global".
+DECODER_PATH = os.environ.get("GRIPNET_B200_DECODER", "global")
 
 
 def _z_resident(z):
