@@ -50,8 +50,8 @@ __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t
   if (i < n) dst[i] = src[idx[i]];
 }
 
-constexpr int kMtThreads = 256;
-constexpr int kMtItems = 4;
+constexpr int kMtThreads = 1024;   // one CTA walks a relation's ranked slice: wide tiles keep the walk short
+constexpr int kMtItems = 8;
 constexpr int kMtTile = kMtThreads * kMtItems;
 
 struct ScanPair {
@@ -63,7 +63,7 @@ __device__ __forceinline__ ScanPair combine(const ScanPair a, const ScanPair b) 
   return ScanPair{a.sum + b.sum, max(a.last, b.last)};
 }
 
-__global__ void __launch_bounds__(kMtThreads) lp_metrics_kernel(const float* __restrict__ pos, int64_t n_pos,
+__global__ void __launch_bounds__(kMtThreads, 1) lp_metrics_kernel(const float* __restrict__ pos, int64_t n_pos,
                                                                 const float* __restrict__ neg,
                                                                 const int32_t* __restrict__ perm,
                                                                 const int32_t* __restrict__ rowptr,
