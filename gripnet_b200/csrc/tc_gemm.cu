@@ -22,8 +22,11 @@
 //       warp 8     allocates TMEM and issues the MMAs (one lane), commits to mbarriers;
 //       warp 9     brings the pre-split image of B for each k-block with ONE bulk
 //                  async copy (cp.async.bulk, TMA engine) completing on the stage's mbarrier;
-//   * B is tiny and shared by every CTA: a prep kernel writes its hi/lo split once per call,
-//     already in the shared-memory layout (k-block major), into the caller's workspace;
+//   * B is shared by every CTA.  A layer's weight matrix (N <= 64 columns, a few KB) is split by the
+//     B-producer warp itself, k-block by k-block, straight into the stage: no extra launch on the
+//     step's dependency chain.  A wide B (the [in, R*out] relation transform of pose-2) is split once
+//     per call by a prep kernel into the caller's workspace, already in the shared-memory layout
+//     (k-block major), and each k-block arrives with ONE bulk async copy;
 //   * 2-3 smem stages, full/empty mbarriers; tcgen05.commit releases a stage when the
 //     MMAs that read it have retired.
 #include "common.cuh"
@@ -51,7 +54,8 @@ struct Params {
   float* C; int64_t ldc;
   const float* addend; int64_t ldd;
   const float* mask; int64_t ldm;
-  const char* b_image;   // [n_tile][k_block][hi|lo][chunk][row][4 floats] (+ plane padding)
+  const char* b_image;   // [n_tile][k_block][hi|lo][chunk][row][4 floats] (+ plane padding); NULL: split B in the kernel
+  const float* B; int64_t ldb; int transB;   // op(B) itself, read by the B producer when b_image == NULL
   int nt;                // columns per N tile (multiple of 16, <= 256)
   int n_kb;              // k-blocks
   int stages;
@@ -342,15 +346,47 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
     }
     __syncwarp();
   } else {
-    // =============================== B producer (bulk async copy) ============
-    if (lane == 0) {
-      const uint32_t bytes = 2 * part_bytes(nt);
-      const char* src = p.b_image + int64_t(tile_n) * p.n_kb * bytes;
+    // =============================== B producer ===============================
+    if (p.b_image != nullptr) {
+      // large B: ONE bulk async copy per k-block of the image a prep kernel split beforehand
+      if (lane == 0) {
+        const uint32_t bytes = 2 * part_bytes(nt);
+        const char* src = p.b_image + int64_t(tile_n) * p.n_kb * bytes;
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          const int s = kb % S, use = kb / S;
+          if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          bulk_g2s(smem + s * stage_sz + 2 * part_bytes(BM), src + int64_t(kb) * bytes, bytes, &full_bar[s]);
+        }
+      }
+    } else {
+      // small B (a layer's weight matrix, a few KB, L2-resident): this warp splits the k-block's slice of
+      // op(B) straight into the stage — no prep kernel, no extra launch on the step's dependency chain
+      const int n_tile0 = tile_n * nt;
       for (int kb = 0; kb < p.n_kb; ++kb) {
         const int s = kb % S, use = kb / S;
         if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-        mbar_arrive_expect_tx(&full_bar[s], bytes);
-        bulk_g2s(smem + s * stage_sz + 2 * part_bytes(BM), src + int64_t(kb) * bytes, bytes, &full_bar[s]);
+        unsigned char* b_hi = smem + s * stage_sz + 2 * part_bytes(BM);
+        unsigned char* b_lo = b_hi + part_bytes(nt);
+        for (int i = lane; i < CHUNKS * nt; i += 32) {
+          const int row = i % nt, c = i / nt;
+          const int n = n_tile0 + row, k = kb * BK + c * 4;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = 0.f;
+            if (n < p.N && k + e < p.K)
+              x = p.transB ? __ldg(p.B + int64_t(n) * p.ldb + k + e) : __ldg(p.B + int64_t(k + e) * p.ldb + n);
+            v[e] = x;
+          }
+          float4 hi, lo;
+          split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+          *reinterpret_cast<float4*>(b_hi + c * plane_bytes(nt) + row * 16) = hi;
+          *reinterpret_cast<float4*>(b_lo + c * plane_bytes(nt) + row * 16) = lo;
+        }
+        fence_proxy_async();               // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
       }
     }
     __syncwarp();
@@ -398,6 +434,10 @@ static Plan make_plan(int M, int N, int K) {
 
 using namespace gn;
 
+// B small enough for the B-producer warp to split it inside the main kernel (one N tile, <= 16 float4 per lane
+// and k-block): no prep launch.  Larger B (the [in, R*out] relation transform of pose-2) keeps the image.
+static bool b_direct(const tc::Plan& pl) { return pl.n_tiles == 1 && pl.nt <= 64; }
+
 extern "C" size_t gn_tc_gemm_workspace_bytes(int32_t M, int32_t N, int32_t K) {
   const tc::Plan pl = tc::make_plan(M, N, K);
   return pl.ok ? align_up(pl.image_bytes) : 0;
@@ -415,16 +455,20 @@ extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const flo
   if (relu_mask && (!al16(relu_mask) || ld_mask % 4 != 0)) return GN_ERR_ARG;
   const tc::Plan pl = tc::make_plan(M, N, K);
   if (!pl.ok) return GN_ERR_ARG;
-  if (!ws || ws_bytes < pl.image_bytes || !al16(ws)) return GN_ERR_WORKSPACE;
+  const bool direct = b_direct(pl);
+  if (!direct && (!ws || ws_bytes < pl.image_bytes || !al16(ws))) return GN_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
-  const int64_t total = int64_t(pl.n_tiles) * pl.n_kb * tc::CHUNKS * pl.nt;
-  GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, B, ldb, transB ? 1 : 0, K, N, pl.nt, pl.n_kb,
-            static_cast<char*>(ws));
+  if (!direct) {
+    const int64_t total = int64_t(pl.n_tiles) * pl.n_kb * tc::CHUNKS * pl.nt;
+    GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, B, ldb, transB ? 1 : 0, K, N, pl.nt,
+              pl.n_kb, static_cast<char*>(ws));
+  }
   tc::Params p;
   p.M = M; p.N = N; p.K = K;
   p.A = A; p.lda = lda; p.C = C; p.ldc = ldc;
   p.addend = addend; p.ldd = ld_addend; p.mask = relu_mask; p.ldm = ld_mask;
-  p.b_image = static_cast<const char*>(ws);
+  p.b_image = direct ? nullptr : static_cast<const char*>(ws);
+  p.B = B; p.ldb = ldb; p.transB = transB ? 1 : 0;
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
   p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
   static std::atomic<int> attr_set{0};
