@@ -84,7 +84,8 @@ def test_tc_gemm_epilogue_and_strided_slices():
 
 
 def test_dispatch_routes_tall_products_to_tensor_cores():
-    """ops.sgemm sends tall plain products to gn_tc_gemm (2 launches: B image + UMMA kernel)."""
+    """ops.sgemm sends tall plain products to gn_tc_gemm: ONE launch when B is a small weight matrix (split
+    inside the kernel by the B-producer warp), two (B image + UMMA kernel) when B is wide."""
     import gripnet_b200 as gb
     from gripnet_b200 import ops
     d = _dev()
@@ -94,5 +95,12 @@ def test_dispatch_routes_tall_products_to_tensor_cores():
     C = torch.empty(m, n, device=d)
     before = gb.launch_count()
     ops.sgemm(False, False, m, n, k, A.data_ptr(), k, W.data_ptr(), n, C.data_ptr(), n, d)
-    assert gb.launch_count() - before == 2
+    assert gb.launch_count() - before == 1
     assert rel_err(C, A.double() @ W.double()) < 2e-6
+    n2 = 80                                              # nt > 64: the image path
+    W2 = torch.randn(k, n2, device=d)
+    C2 = torch.empty(m, n2, device=d)
+    before = gb.launch_count()
+    ops.sgemm(False, False, m, n2, k, A.data_ptr(), k, W2.data_ptr(), n2, C2.data_ptr(), n2, d)
+    assert gb.launch_count() - before == 2
+    assert rel_err(C2, A.double() @ W2.double()) < 2e-6
