@@ -1,6 +1,8 @@
 // K9/K10/K11: DistMult link decoder (fused gather-multiply-reduce), its
 // deterministic backward, and the softmax pieces of the multi-class decoder.
 // Reference arithmetic restated: gripnet/decoder.py:19-23, :38-45.
+#include <cstdlib>
+
 #include "rowsplit.cuh"
 
 namespace gn {
@@ -106,8 +108,9 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const gn_csr csr, con
     const int s1 = s0 + EPI;
     const bool has1 = s1 < ci.end;
     // ---- indices of both entries
-    const int e0 = __ldg(ent_eid + s0);
-    const int e1 = has1 ? __ldg(ent_eid + s1) : 0;
+    // ent_eid == nullptr: entry s IS edge s (a relation-major edge list walked by its relation CSR)
+    const int e0 = ent_eid ? __ldg(ent_eid + s0) : s0;
+    const int e1 = has1 ? (ent_eid ? __ldg(ent_eid + s1) : s1) : 0;
     const float* pa0;
     const float* pa1 = z;
     const float* pb0 = z;
@@ -230,9 +233,14 @@ struct WidthPlan {
 };
 
 // lanes-per-entry and vectors-per-lane for a D-wide row (at most kMaxNV vectors per lane)
-inline WidthPlan plan_width(int D, bool can_vec4) {
+inline WidthPlan plan_width(int D, bool can_vec4, bool wide = false) {
   WidthPlan p{can_vec4 ? 4 : 1, 0, 0, true};
   const int units = (D + p.vec - 1) / p.vec;
+  if (wide && can_vec4 && units > 8 && units <= 24) {   // 8 lanes x 3 vectors: fewer registers, more warps per SM
+    p.lpe = 8;
+    p.nv = 3;
+    return p;
+  }
   if (units <= 4 * kMaxNV) p.lpe = 4;
   else if (units <= 32 * kMaxNV) p.lpe = 32;
   else p.ok = false;
@@ -251,7 +259,15 @@ static int launch_bwd(const gn_csr& csr, const int32_t* ent_a, const int32_t* en
   if (csr.n_chunks > csr.n_rows && !partial) return GN_ERR_ARG;
   const bool v4 = (D % 4 == 0) && (ldz % 4 == 0) && (ldo % 4 == 0) && aligned16(z) && aligned16(outp) &&
                   (!w || aligned16(w)) && (!partial || aligned16(partial));
-  const WidthPlan p = plan_width(D, v4);
+  static const int wide_mode = [] {
+    const char* e = getenv("GRIPNET_B200_DECODER_LPE8");   // "z", "w", "zw": experiment switch
+    int m = 0;
+    if (e) {
+      for (const char* c = e; *c; ++c) m |= (*c == 'z') ? 1 : (*c == 'w') ? 2 : 0;
+    }
+    return m;
+  }();
+  const WidthPlan p = plan_width(D, v4, (wide_mode & (MODE == 0 ? 1 : 2)) != 0);
   if (!p.ok) return GN_ERR_ARG;
   const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
 #define GN_BWD_CASE(L, V, N)                                                                                         \
@@ -263,6 +279,7 @@ static int launch_bwd(const gn_csr& csr, const int32_t* ent_a, const int32_t* en
 #define GN_BWD_CASES(L, V) GN_BWD_CASE(L, V, 1) GN_BWD_CASE(L, V, 2) GN_BWD_CASE(L, V, 4) GN_BWD_CASE(L, V, 5) \
   GN_BWD_CASE(L, V, 8)
   GN_BWD_CASES(4, 4)
+  GN_BWD_CASE(8, 4, 3)
   GN_BWD_CASES(32, 4)
   GN_BWD_CASES(4, 1)
   GN_BWD_CASES(32, 1)
@@ -329,7 +346,7 @@ int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64
                       const float* coef, const float* z, int64_t ldz, int32_t D, float* dw, float* partial,
                       void* stream) {
   if (!rel_csr || !z || !dw || D <= 0) return GN_ERR_ARG;
-  if (rel_csr->nnz > 0 && (!rel_eid || !src || !dst || !coef)) return GN_ERR_ARG;
+  if (rel_csr->nnz > 0 && (!src || !dst || !coef)) return GN_ERR_ARG;      // rel_eid == NULL: identity order
   return launch_bwd<1>(*rel_csr, nullptr, nullptr, rel_eid, src, dst, coef, z, ldz, D, nullptr, dw, D, partial,
                        as_stream(stream));
 }

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kResThreads, 1) distmult_bwd_res_kernel(
       int ia = 0, ib = 0;        // MODE 0: other, rel;  MODE 1: src, dst
       float g = 0.f;
       if (mine < ci.end) {
-        const int e = __ldg(ent_eid + mine);
+        const int e = ent_eid ? __ldg(ent_eid + mine) : mine;
         g = __ldg(coef + e);
         if (MODE == 0) {
           ia = __ldg(ent_a + mine);
@@ -283,7 +283,7 @@ int gn_distmult_bwd_w_resident(const gn_csr* rel_csr, const int32_t* rel_eid, co
                                const float* coef, const float* z, int64_t ldz, int32_t n_nodes, int32_t D, float* dw,
                                float* partial, void* stream) {
   if (!rel_csr || !z || !dw || D <= 0 || n_nodes <= 0) return GN_ERR_ARG;
-  if (rel_csr->nnz > 0 && (!rel_eid || !src || !dst || !coef)) return GN_ERR_ARG;
+  if (rel_csr->nnz > 0 && (!src || !dst || !coef)) return GN_ERR_ARG;      // rel_eid == NULL: identity order
   return launch_bwd_res(1, *rel_csr, nullptr, nullptr, rel_eid, src, dst, coef, z, ldz, n_nodes, D, nullptr, dw, D,
                         partial, as_stream(stream));
 }

@@ -32,6 +32,13 @@ def _host_int(t):
     return int(t.item())
 
 
+def _host_bool(t):
+    s = streams.override()
+    if s is not None:
+        s.synchronize()
+    return bool(t.item())
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -326,6 +333,11 @@ class IndexStruct:
         _lib.check(lib.gn_index_prep(_ptr(idx) if n else None, n, n_nodes, _ptr(rowptr), _ptr(self.perm), _ptr(ws),
                                      ws.numel(), _stream()), "gn_index_prep")
         self.csr = Csr(rowptr, self.perm, None, n_nodes, max(n, 1), n, exact=exact)
+        # a non-decreasing index list (relation-major edge types) sorts to itself: consumers may then walk
+        # the list in place instead of through `perm`.  Known only for structures built outside a capture
+        # (one host read at build time); structures built inside a captured graph keep the general path.
+        self.identity = bool(exact and n > 0 and _host_bool(
+            (self.perm[:n] == torch.arange(n, dtype=torch.int32, device=dev)).all()))
 
 
 # --------------------------------------------------------------------------

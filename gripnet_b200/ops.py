@@ -548,6 +548,7 @@ def _distmult_check(z, weight, edge_index, edge_type):
 # NOT faster — the decoder is bound by the latency of its index / coefficient streams at the occupancy one
 # 206 KB CTA per SM allows, not by the L1 row gathers — so the default stays "global".
 DECODER_PATH = os.environ.get("GRIPNET_B200_DECODER", "global")
+DW_IDENTITY = os.environ.get("GRIPNET_B200_DW_IDENTITY", "1") != "0"
 
 
 def _z_resident(z):
@@ -610,12 +611,13 @@ def _distmult_dw(dw, edge_type_key, ei, coef, z, alt=False):
     n, d, r, e = z.size(0), z.size(1), dw.size(0), ei.size(1)
     rs = rel_struct(edge_type_key, r)
     part = rs.csr.partial(d)
+    perm = None if (rs.identity and DW_IDENTITY) else _ptr(rs.perm)     # relation-major list: entry s is edge s
     if e and _z_resident(z):
         _lib.check(_lib.load().gn_distmult_bwd_w_resident(
-            rs.csr.alt_ref() if alt else rs.csr.ref, _ptr(rs.perm), _ptr(ei[0]), _ptr(ei[1]), _ptr(coef), z.data_ptr(),
+            rs.csr.alt_ref() if alt else rs.csr.ref, perm, _ptr(ei[0]), _ptr(ei[1]), _ptr(coef), z.data_ptr(),
             z.stride(0) if n > 1 else d, n, d, dw.data_ptr(), _ptr(part), _stream()), "gn_distmult_bwd_w_resident")
         return
-    _lib.check(_lib.load().gn_distmult_bwd_w(rs.csr.alt_ref() if alt else rs.csr.ref, _ptr(rs.perm), _ptr(ei[0]) if e else None,
+    _lib.check(_lib.load().gn_distmult_bwd_w(rs.csr.alt_ref() if alt else rs.csr.ref, perm, _ptr(ei[0]) if e else None,
                                              _ptr(ei[1]) if e else None, _ptr(coef), z.data_ptr(),
                                              z.stride(0) if n > 1 else d, d, dw.data_ptr(), _ptr(part), _stream()),
                "gn_distmult_bwd_w")

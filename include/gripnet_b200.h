@@ -202,7 +202,8 @@ int gn_distmult_coef(const float* grad_out, const float* out, int64_t n_edges, i
 int gn_distmult_bwd_z(const gn_csr* node_csr, const int32_t* ent_other, const int32_t* ent_rel,
                       const int32_t* ent_eid, const float* coef, const float* z, int64_t ldz,
                       int32_t D, const float* w, float* dz, int64_t lddz, float* partial, void* stream);
-/* dw[r] = sum_{e in relation r} coef[e] * z[src_e] .* z[dst_e] */
+/* dw[r] = sum_{e in relation r} coef[e] * z[src_e] .* z[dst_e];  rel_eid == NULL: entry s of the relation
+ * CSR is edge s (a relation-major edge list, as the reference builds them, GripNet-pose.py:54-56) */
 int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64_t* src,
                       const int64_t* dst, const float* coef, const float* z, int64_t ldz,
                       int32_t D, float* dw, float* partial, void* stream);
