@@ -259,12 +259,14 @@ static int launch_bwd(const gn_csr& csr, const int32_t* ent_a, const int32_t* en
   if (csr.n_chunks > csr.n_rows && !partial) return GN_ERR_ARG;
   const bool v4 = (D % 4 == 0) && (ldz % 4 == 0) && (ldo % 4 == 0) && aligned16(z) && aligned16(outp) &&
                   (!w || aligned16(w)) && (!partial || aligned16(partial));
+  // 8 lanes x 3 vectors per entry for the node-row (dz) walk: 80 registers instead of 128, three CTAs per SM
+  // instead of two (measured: 37.8 -> 35.5 us at pose-0 size; the relation-row (dw) walk is slower that way:
+  // 40.8 -> 52.7 us).  GRIPNET_B200_DECODER_LPE8 = "", "z", "w" or "zw" overrides the choice.
   static const int wide_mode = [] {
-    const char* e = getenv("GRIPNET_B200_DECODER_LPE8");   // "z", "w", "zw": experiment switch
+    const char* e = getenv("GRIPNET_B200_DECODER_LPE8");
+    if (!e) return 1;
     int m = 0;
-    if (e) {
-      for (const char* c = e; *c; ++c) m |= (*c == 'z') ? 1 : (*c == 'w') ? 2 : 0;
-    }
+    for (const char* c = e; *c; ++c) m |= (*c == 'z') ? 1 : (*c == 'w') ? 2 : 0;
     return m;
   }();
   const WidthPlan p = plan_width(D, v4, (wide_mode & (MODE == 0 ? 1 : 2)) != 0);
