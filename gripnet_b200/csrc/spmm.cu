@@ -7,11 +7,13 @@
 //    32/LPE rows per step, LPE steps unrolled -> LPE loads in flight per lane);
 //  * bias / root addend / ReLU / column-slice write fused in the epilogue;
 //  * no data atomics; summation order fixed -> deterministic fwd and bwd.
+#include <cstdlib>
+
 #include "rowsplit.cuh"
 
 namespace gn {
 
-template <int LPE, int VEC>
+template <int LPE, int VEC, bool PIPE>
 __global__ void __launch_bounds__(256) spmm_kernel(const gn_csr csr, const float* __restrict__ x, int64_t ldx, int F,
                                                    const float* __restrict__ row_scale, const float* __restrict__ bias,
                                                    const float* addend, int64_t ld_addend, int relu, float* out,
@@ -28,13 +30,36 @@ __global__ void __launch_bounds__(256) spmm_kernel(const gn_csr csr, const float
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0].v[i] = 0.f;
 
+  // software pipeline: the (col, val) pairs of batch b+1 are requested before the row gathers of batch b, so a
+  // row costs one index round trip plus one gather round trip per batch instead of two dependent ones
+  int c_next = -1;
+  float w_next = 0.f;
+  if (PIPE) {
+    const int first = ci.beg + lane;
+    if (first < ci.end) {
+      c_next = __ldg(csr.col + first);
+      w_next = csr.val ? __ldg(csr.val + first) : 1.0f;
+    }
+  }
   for (int base = ci.beg; base < ci.end; base += 32) {
-    const int mine = base + lane;
     int c = -1;
     float w = 0.f;
-    if (mine < ci.end) {
-      c = __ldg(csr.col + mine);
-      w = csr.val ? __ldg(csr.val + mine) : 1.0f;
+    if (PIPE) {
+      c = c_next;
+      w = w_next;
+      c_next = -1;
+      w_next = 0.f;
+      const int nxt = base + 32 + lane;
+      if (nxt < ci.end) {
+        c_next = __ldg(csr.col + nxt);
+        w_next = csr.val ? __ldg(csr.val + nxt) : 1.0f;
+      }
+    } else {
+      const int mine = base + lane;
+      if (mine < ci.end) {
+        c = __ldg(csr.col + mine);
+        w = csr.val ? __ldg(csr.val + mine) : 1.0f;
+      }
     }
 #pragma unroll
     for (int t = 0; t < LPE; ++t) {
@@ -80,10 +105,18 @@ static int launch_spmm(int lpe, const gn_csr& csr, const float* x, int64_t ldx, 
                        const float* bias, const float* addend, int64_t ld_addend, int relu, float* out, int64_t ldo,
                        float* partial, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
-#define GN_SPMM_CASE(L)                                                                                          \
-  case L:                                                                                                        \
-    GN_LAUNCH((spmm_kernel<L, VEC>), grid, 256, 0, st, csr, x, ldx, F, row_scale, bias, addend, ld_addend, relu, \
-              out, ldo, partial);                                                                                \
+  static const bool pipe = [] {
+    const char* e = getenv("GRIPNET_B200_SPMM_PIPE");
+    return e ? (e[0] != '0') : false;
+  }();
+#define GN_SPMM_CASE(L)                                                                                       \
+  case L:                                                                                                     \
+    if (pipe)                                                                                                 \
+      GN_LAUNCH((spmm_kernel<L, VEC, true>), grid, 256, 0, st, csr, x, ldx, F, row_scale, bias, addend,       \
+                ld_addend, relu, out, ldo, partial);                                                          \
+    else                                                                                                      \
+      GN_LAUNCH((spmm_kernel<L, VEC, false>), grid, 256, 0, st, csr, x, ldx, F, row_scale, bias, addend,      \
+                ld_addend, relu, out, ldo, partial);                                                          \
     break;
   switch (lpe) {
     GN_SPMM_CASE(1)

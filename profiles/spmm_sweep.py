@@ -35,7 +35,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1111)
-    for name, n, e, F, kind in SHAPES:
+    shapes = SHAPES[:4] if "--small" in sys.argv else SHAPES
+    for name, n, e, F, kind in shapes:
         if kind == "uniform":
             ei = torch.randint(0, n, (2, e), device=dev, generator=gen)
         else:
