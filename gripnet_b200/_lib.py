@@ -18,7 +18,7 @@ class GnCsr(C.Structure):
     """Mirror of ``gn_csr`` (include/gripnet_b200.h)."""
     _fields_ = [
         ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("nnz", C.c_int32), ("chunk_len", C.c_int32),
-        ("n_chunks", C.c_int32), ("_pad", C.c_int32),
+        ("n_chunks", C.c_int32), ("flags", C.c_int32),
         ("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p),
         ("chunk_ptr", C.c_void_p), ("chunk_row", C.c_void_p), ("chunk_beg", C.c_void_p),
         ("row_counter", C.c_void_p),
@@ -95,6 +95,7 @@ SIGNATURES = {
 }
 
 EW_COPY, EW_ABS, EW_RELU, EW_ADD = 0, 1, 2, 3
+CSR_ROW_IS_CHUNK = 1
 
 _lib = None
 

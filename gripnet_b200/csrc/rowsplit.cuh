@@ -82,6 +82,13 @@ struct ChunkInfo {
 // chunk `warp` of the work list (false when it lies beyond the list)
 __device__ __forceinline__ bool chunk_info_at(const gn_csr& csr, int warp, ChunkInfo& ci) {
   if (warp >= csr.n_chunks) return false;
+  if (csr.flags & GN_CSR_ROW_IS_CHUNK) {   // chunk i is row i: no chunk tables, one round trip
+    ci.chunk = ci.row = ci.first_chunk = warp;
+    ci.beg = __ldg(csr.rowptr + warp);
+    ci.end = __ldg(csr.rowptr + warp + 1);
+    ci.n_chunks_of_row = 1;
+    return true;
+  }
   if (warp >= __ldg(csr.chunk_ptr + csr.n_rows)) return false;
   ci.chunk = warp;
   ci.row = __ldg(csr.chunk_row + warp);

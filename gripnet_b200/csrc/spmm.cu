@@ -14,7 +14,7 @@
 namespace gn {
 
 template <int LPE, int VEC, bool PIPE>
-__global__ void __launch_bounds__(256) spmm_kernel(const gn_csr csr, const float* __restrict__ x, int64_t ldx, int F,
+__global__ void __launch_bounds__(256, (LPE == 16 ? 5 : 6)) spmm_kernel(const gn_csr csr, const float* __restrict__ x, int64_t ldx, int F,
                                                    const float* __restrict__ row_scale, const float* __restrict__ bias,
                                                    const float* addend, int64_t ld_addend, int relu, float* out,
                                                    int64_t ldo, float* __restrict__ partial) {

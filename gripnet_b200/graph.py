@@ -7,6 +7,7 @@ counterpart of ``myGCN.cached_result`` (reference ``gripnet/layers.py:83-90``).
 All arrays live in HBM as int32 / fp32 tensors owned by these objects.
 """
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import torch
@@ -14,6 +15,7 @@ import torch
 from . import _lib, streams
 
 _SM_COUNT = 148
+ROW_IS_CHUNK = os.environ.get("GRIPNET_B200_ROW_IS_CHUNK", "1") != "0"
 
 
 def _stream():
@@ -91,7 +93,9 @@ class Csr:
             self.n_chunks = _host_int(self.chunk_ptr[self.n_rows]) if self.n_rows > 0 else 0
         else:
             self.n_chunks = cap - 1 if self.n_rows > 0 else 0
-        self.c = _lib.GnCsr(self.n_rows, self.n_cols, self.nnz, self.chunk_len, self.n_chunks, 0,
+        # every row fits one chunk (known exactly): kernels read the row bounds straight from rowptr
+        self.flags = _lib.CSR_ROW_IS_CHUNK if (exact and ROW_IS_CHUNK and self.n_chunks == self.n_rows) else 0
+        self.c = _lib.GnCsr(self.n_rows, self.n_cols, self.nnz, self.chunk_len, self.n_chunks, self.flags,
                             _ptr(rowptr), _ptr(col), _ptr(val), _ptr(self.chunk_ptr), _ptr(self.chunk_row),
                             _ptr(self.chunk_beg), _ptr(self.row_counter))
         self.ref = C.byref(self.c)
@@ -103,7 +107,7 @@ class Csr:
         edges share the relation CSR)."""
         if self._alt is None:
             rc = torch.zeros(max(self.n_rows, 1), dtype=torch.int32, device=self.rowptr.device)
-            c = _lib.GnCsr(self.n_rows, self.n_cols, self.nnz, self.chunk_len, self.n_chunks, 0,
+            c = _lib.GnCsr(self.n_rows, self.n_cols, self.nnz, self.chunk_len, self.n_chunks, self.flags,
                            _ptr(self.rowptr), _ptr(self.col), _ptr(self.val), _ptr(self.chunk_ptr),
                            _ptr(self.chunk_row), _ptr(self.chunk_beg), _ptr(rc))
             self._alt = (c, C.byref(c), rc)

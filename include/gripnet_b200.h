@@ -56,7 +56,9 @@ typedef struct {
   int32_t nnz;             /* stored entries (host copy; may be an upper bound)      */
   int32_t chunk_len;       /* max entries per chunk                                  */
   int32_t n_chunks;        /* chunks to launch (exact or an upper bound)             */
-  int32_t _pad;
+  int32_t flags;           /* GN_CSR_ROW_IS_CHUNK: every row is exactly one chunk (chunk i == row i, n_chunks ==
+                              n_rows, known exactly on the host): kernels then take the row bounds from rowptr
+                              alone and skip the chunk tables (one dependent round trip less per warp)      */
   const int32_t* rowptr;   /* [n_rows+1]                                             */
   const int32_t* col;      /* [nnz] gathered-row index                               */
   const float* val;        /* [nnz] per-entry coefficient, or NULL for all-ones      */
@@ -65,6 +67,7 @@ typedef struct {
   const int32_t* chunk_beg;/* [n_chunks] first entry of each chunk                   */
   int32_t* row_counter;    /* [n_rows] zero-initialised; left zero by every call     */
 } gn_csr;
+enum { GN_CSR_ROW_IS_CHUNK = 1 };
 
 /* ---- K1: graph preprocessing ------------------------------------------- */
 
