@@ -1,0 +1,88 @@
+"""Drop-in boundary: the module API of ``gripnet_b200`` against the public surface of the
+UNMODIFIED reference, recorded in ``tests/golden/api_surface.json`` by ``tests/golden/make_api_surface.py``:
+same classes, same constructor / ``forward`` parameter names, order and defaults, same ``state_dict`` keys and
+shapes, same ``gripnet.utils`` functions.  Extra trailing OPTIONAL parameters are allowed on this side."""
+import inspect
+import json
+import os
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SURFACE = json.load(open(os.path.join(HERE, "golden", "api_surface.json")))
+
+
+def _params(fn):
+    out = []
+    for p in inspect.signature(fn).parameters.values():
+        if p.name == "self" or p.kind in (p.VAR_KEYWORD, p.VAR_POSITIONAL):
+            continue
+        out.append([p.name, None if p.default is p.empty else repr(p.default)])
+    return out
+
+
+def _assert_compatible(ours, ref, what):
+    assert len(ours) >= len(ref), (what, ours, ref)
+    for (on, od), (rn, rd) in zip(ours, ref):
+        assert on == rn, (what, on, rn)
+        assert od == rd, (what, on, od, rd)
+    for name, default in ours[len(ref):]:
+        assert default is not None, f"{what}: extra parameter {name} must be optional"
+
+
+@pytest.mark.parametrize("name", sorted(SURFACE["classes"]))
+def test_class_signatures_match_the_reference(name):
+    import gripnet_b200 as gb
+    ref = SURFACE["classes"][name]
+    mod = getattr(gb, ref["module"])
+    cls = getattr(mod, name)
+    assert getattr(gb, name) is cls                       # also exported at package level
+    _assert_compatible(_params(cls.__init__), ref["init"], f"{name}.__init__")
+    _assert_compatible(_params(cls.forward), ref["forward"], f"{name}.forward")
+    if "norm" in ref:
+        _assert_compatible(_params(cls.norm), ref["norm"], f"{name}.norm")
+
+
+def test_utils_functions_match_the_reference():
+    from gripnet_b200 import utils
+    assert utils.EPS == SURFACE["utils_constants"]["EPS"]
+    for name, ref in SURFACE["utils"].items():
+        assert hasattr(utils, name), f"gripnet.utils.{name} is missing"
+        _assert_compatible(_params(getattr(utils, name)), ref, f"utils.{name}")
+
+
+def test_state_dict_keys_and_shapes_match_the_reference():
+    from gripnet_b200 import decoder, layers
+    ours = {
+        "myGCN": layers.myGCN(4, 3), "myRGCN": layers.myRGCN(4, 3, 2, 2, False),
+        "homoGraph": layers.homoGraph([4, 3, 2], start_graph=True, in_dim=5),
+        "homoGraph_rel": layers.homoGraph([4, 3], multi_relational=True, n_rela=2, n_base=2),
+        "interGraph": layers.interGraph(4, 3, 6, target_feat_dim=5),
+        "interGraph_down": layers.interGraph(4, 3, 6, target_feat_dim=5),
+        "multiRelaInnerProductDecoder": decoder.multiRelaInnerProductDecoder(4, 3),
+        "multiClassInnerProductDecoder": decoder.multiClassInnerProductDecoder(4, 3),
+    }
+    for k, ref in SURFACE["state_dict"].items():
+        got = {n: list(t.shape) for n, t in ours[k].state_dict().items()}
+        assert got == ref, (k, got, ref)
+
+
+def test_install_as_gripnet_aliases_the_reference_import_names():
+    import importlib
+    import sys
+    import gripnet_b200 as gb
+    saved = {k: v for k, v in sys.modules.items() if k == "gripnet" or k.startswith("gripnet.")}
+    try:
+        gb.install_as_gripnet()
+        from gripnet.layers import homoGraph, interGraph          # the scripts' own import lines
+        from gripnet.decoder import multiClassInnerProductDecoder, multiRelaInnerProductDecoder
+        from gripnet.utils import EPS, micro_macro, process_data_multiclass, sparse_id
+        assert homoGraph is gb.layers.homoGraph and interGraph is gb.layers.interGraph
+        assert multiRelaInnerProductDecoder is gb.decoder.multiRelaInnerProductDecoder
+        assert multiClassInnerProductDecoder is gb.decoder.multiClassInnerProductDecoder
+        assert EPS == 1e-13 and callable(micro_macro) and callable(process_data_multiclass) and callable(sparse_id)
+        assert importlib.import_module("gripnet.encoder").RGCN is gb.encoder.RGCN
+    finally:
+        for k in [k for k in sys.modules if k == "gripnet" or k.startswith("gripnet.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
