@@ -123,38 +123,22 @@ def _sampler_for(pos_edge_index, num_nodes, range_list):
     return hit[0]
 
 
-def _host_negative_sampling(pos_edge_index, num_nodes, generator=None):
-    rs = generator if generator is not None else np.random
-    pos = pos_edge_index.detach().cpu().numpy().astype(np.int64)
-    taken = np.unique(pos[0] * num_nodes + pos[1])
-    code = rs.randint(0, num_nodes * num_nodes, size=pos.shape[1]).astype(np.int64)
-    bad = np.isin(code, taken)
-    while bad.any():
-        code[bad] = rs.randint(0, num_nodes * num_nodes, size=int(bad.sum()))
-        bad = np.isin(code, taken)
-    return torch.from_numpy(np.stack([code // num_nodes, code % num_nodes]))
+def negative_sampling(pos_edge_index, num_nodes):
+    """Uniform node pairs that are not positive edges, one per positive (utils.py:98-112), sampled on the
+    device (``NegativeSampler``, cached per edge tensor; successive calls give successive epochs) — no
+    device<->host round trip.  Same distribution as the reference; the RNG stream is this package's own
+    (Philox4x32-10, seeded from ``torch.initial_seed()``).  CUDA tensors only: there is no CPU path."""
+    from .graph import require_cuda
+    require_cuda(pos_edge_index, "pos_edge_index", torch.int64)
+    return _sampler_for(pos_edge_index, num_nodes, None).sample()
 
 
-def negative_sampling(pos_edge_index, num_nodes, generator=None):
-    """Uniform node pairs that are not positive edges, one per positive (utils.py:98-112).
-
-    CUDA ``pos_edge_index``: sampled on the device (``NegativeSampler``, cached per edge tensor; successive
-    calls give successive epochs) — no device<->host round trip.  CPU tensors (data preparation): the
-    reference's numpy procedure with ``generator`` (a ``numpy.random.RandomState``) or the global numpy
-    RNG.  Same distribution as the reference either way; the RNG streams are this package's own.
-    """
-    if pos_edge_index.is_cuda:
-        return _sampler_for(pos_edge_index, num_nodes, None).sample()
-    return _host_negative_sampling(pos_edge_index, num_nodes, generator)
-
-
-def typed_negative_sampling(pos_edge_index, num_nodes, range_list, generator=None):
+def typed_negative_sampling(pos_edge_index, num_nodes, range_list):
     """Per-relation negative sampling (utils.py:115-119): a draw is rejected only if it is a positive
-    pair of the SAME ``range_list`` slice."""
-    if pos_edge_index.is_cuda:
-        return _sampler_for(pos_edge_index, num_nodes, range_list).sample()
-    parts = [_host_negative_sampling(pos_edge_index[:, int(s):int(e)], num_nodes, generator) for s, e in range_list]
-    return torch.cat(parts, dim=1)
+    pair of the SAME ``range_list`` slice.  CUDA tensors only."""
+    from .graph import require_cuda
+    require_cuda(pos_edge_index, "pos_edge_index", torch.int64)
+    return _sampler_for(pos_edge_index, num_nodes, range_list).sample()
 
 
 # ---- host-side data preparation (gripnet/utils.py:13-25, :55-95, :151-272): not kernels; present so a script

@@ -70,17 +70,15 @@ def test_oracle_is_uniform_over_the_free_pairs():
     assert chi2 < 160, chi2          # 95 dof: mean 95, sd 13.8 -> > 4.7 sd would fail
 
 
-def test_host_utils_keep_the_reference_contract():
+def test_sampling_utils_have_no_cpu_path():
+    """``gripnet.utils.negative_sampling`` / ``typed_negative_sampling`` keep the reference's signatures but run
+    on the device only: CPU tensors are refused like everywhere else in the package."""
     import gripnet_b200.utils as u
-    rs = np.random.RandomState(0)
-    pos = torch.from_numpy(rs.randint(0, 30, (2, 200)))
-    neg = u.negative_sampling(pos, 30, np.random.RandomState(1))
-    assert neg.shape == pos.shape and neg.dtype == torch.int64
-    assert not np.isin((neg[0] * 30 + neg[1]).numpy(), (pos[0] * 30 + pos[1]).numpy()).any()
-    rl = torch.tensor([[0, 120], [120, 200]])
-    t = u.typed_negative_sampling(pos, 30, rl, np.random.RandomState(2))
-    for s, e in rl.tolist():
-        assert not np.isin((t[0, s:e] * 30 + t[1, s:e]).numpy(), (pos[0, s:e] * 30 + pos[1, s:e]).numpy()).any()
+    pos = torch.from_numpy(np.random.RandomState(0).randint(0, 30, (2, 200)))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        u.negative_sampling(pos, 30)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        u.typed_negative_sampling(pos, 30, torch.tensor([[0, 120], [120, 200]]))
 
 
 # ------------------------------------------------------------------------------------------------
