@@ -432,7 +432,10 @@ def run_cuda(args):
     io = w["io"]
     e2e_mode = "pipelined"
     e2e_ms = None
-    if os.environ.get("GRIPNET_BENCH_E2E", "pipelined") == "pipelined" and not args.eager:
+    # double-buffered copies at N = 1 (measured and checked there); N > 1 keeps the serial loop unless forced:
+    # a rank that rejects the pipelined run alone would leave the others inside the step's collectives
+    e2e_want = os.environ.get("GRIPNET_BENCH_E2E", "pipelined" if world == 1 else "serial")
+    if e2e_want == "pipelined" and not args.eager:
         good, detail = 1, ""
         try:
             e2e_pipelined(io, step, 4, flush)                    # warm-up of the pipeline
