@@ -69,7 +69,7 @@ def main():
             te = metrics.nc_metrics(test_cls, pred, g["n_class"])
         tr = trainer.f1.cpu()
         te = te.cpu()
-        hist[epoch] = torch.tensor([float(loss), float(tr[0]), float(tr[1]), float(te[0]), float(te[1])])
+        hist[epoch] = torch.tensor([float(loss.detach()), float(tr[0]), float(tr[1]), float(te[0]), float(te[1])])
         print("{:3d}   loss:{:0.4f}   train micro:{:0.4f} macro:{:0.4f}   test micro:{:0.4f} macro:{:0.4f}   "
               "time:{:0.3f}".format(epoch, *hist[epoch].tolist(), time.time() - t0))
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)

@@ -53,7 +53,7 @@ def main():
     losses = torch.empty(args.epochs, device=dev)
     for epoch in range(args.epochs):
         t0 = time.time()
-        losses[epoch] = trainer.train_epoch()
+        losses[epoch] = trainer.train_epoch().detach()
         train_rec[epoch] = trainer.record
         with torch.no_grad():                               # test(z), GripNet-pose.py:174-199
             z = trainer.z.detach()
@@ -62,7 +62,7 @@ def main():
             metrics.lp_metrics(pos, neg, test["dd_range_list"], out=test_rec[epoch])
         tr, te = train_rec[epoch].nanmean(dim=1).tolist(), test_rec[epoch].nanmean(dim=1).tolist()   # one sync per epoch
         print("{:3d}   loss:{:0.4f}   train auprc:{:0.4f} auroc:{:0.4f} ap:{:0.4f}   test auprc:{:0.4f} auroc:{:0.4f} "
-              "ap:{:0.4f}   time:{:0.3f}".format(epoch, float(losses[epoch]), *tr, *te, time.time() - t0))
+              "ap:{:0.4f}   time:{:0.3f}".format(epoch, float(losses[epoch].detach()), *tr, *te, time.time() - t0))
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
     torch.save({k: v.cpu() for k, v in model.state_dict().items()}, args.out + "-model.pt")
     torch.save({"train_record": train_rec.cpu(), "test_record": test_rec.cpu(), "loss": losses.cpu()}, args.out + "-record.pt")
