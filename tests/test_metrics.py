@@ -164,3 +164,31 @@ def test_device_nc_metrics_and_argmax():
     np.testing.assert_allclose(got, om.micro_macro_acc(t, score.argmax(1)), rtol=1e-12)
     bad = nc_metrics(torch.tensor(t, device="cuda") + 8, pred, 8).cpu().numpy()
     assert np.isnan(bad).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# property tests of the oracle against scikit-learn (CPU)
+# ------------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.lists(st.tuples(st.booleans(), st.integers(0, 12)), min_size=2, max_size=60))
+def test_oracle_equals_sklearn_on_arbitrary_tie_patterns(items):
+    """Scores drawn from 13 values force every kind of tie group (all-positive, all-negative, mixed, first, last)."""
+    y = np.array([1.0 if a else 0.0 for a, _ in items])
+    if y.min() == y.max():
+        return                                         # sklearn refuses single-class problems
+    s = np.array([b / 12.0 for _, b in items], dtype=np.float32)
+    np.testing.assert_allclose(om.auprc_auroc_ap(y, s), _sk_auprc_auroc_ap(y, s), rtol=1e-12, atol=1e-14)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 5), st.integers(0, 5)), min_size=1, max_size=80))
+def test_oracle_f1_equals_sklearn_on_arbitrary_label_sets(pairs):
+    t = np.array([a for a, _ in pairs])
+    p = np.array([b for _, b in pairs])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = (skm.f1_score(t, p, average="micro"), skm.f1_score(t, p, average="macro"), skm.accuracy_score(t, p))
+    np.testing.assert_allclose(om.micro_macro_acc(t, p), want, rtol=1e-12, atol=1e-15)
