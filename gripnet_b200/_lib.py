@@ -67,6 +67,10 @@ SIGNATURES = {
     "gn_distmult_fwd_resident": (_INT, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _INT, _P, _P]),
     "gn_distmult_bwd_z_resident": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I64, _P, _P]),
     "gn_distmult_bwd_w_resident": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
+    "gn_distmult_dense_scale": (_INT, [_P, _I64, _I32, _I32, _P, _I32, _P, _P]),
+    "gn_distmult_dense_scores": (_INT, [_P, _I32, _P, _P, _P, _I64, _INT, _P, _P]),
+    "gn_distmult_dense_coef": (_INT, [_P, _P, _P, _P, _P, _I32, _I32, _INT, _P, _P]),
+    "gn_distmult_dense_grads": (_INT, [_P, _I32, _I32, _I32, _P, _I64, _P, _P, _I64, _P, _P]),
     "gn_softmax_fwd": (_INT, [_P, _I64, _I32, _P, _P]),
     "gn_softmax_bwd": (_INT, [_P, _P, _I64, _I32, _P, _P]),
     "gn_map2d": (_INT, [_INT, _P, _I64, _P, _I64, _I64, _I32, _P]),

@@ -707,6 +707,71 @@ class DistMultPair(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------
+# dense-relation decoder — EXPERIMENTAL (not yet run on hardware; GRIPNET_B200_DECODER=dense selects it)
+# ----------------------------------------------------------------------------
+_DENSE_MAX_BYTES = 512 << 20          # S and C are [R, n, n] fp32 each
+
+
+def dense_decoder_ok(z, w):
+    return DECODER_PATH == "dense" and w.size(0) * z.size(0) * z.size(0) * 4 <= _DENSE_MAX_BYTES
+
+
+class DistMultPairDense(torch.autograd.Function):
+    """``DistMultPair`` for a small task supervertex with dense relation slices (csrc/decoder_dense.cu):
+    ``S_r = (z .* w_r) z^T`` once for both edge lists, scores by a 4-byte gather; backward through the summed
+    coefficient matrices ``C_r`` of BOTH lists and one batched product ``T_r = C_r z``."""
+
+    @staticmethod
+    def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid):
+        lib = _lib.load()
+        z, w, pi, et = _distmult_check(z, weight, pos_index, edge_type)
+        _, _, ni, _ = _distmult_check(z, weight, neg_index, edge_type)
+        n, d, r, e = z.size(0), z.size(1), w.size(0), pi.size(1)
+        dev, ldz = z.device, (z.stride(0) if z.size(0) > 1 else z.size(1))
+        zw = torch.empty((r, n, d), dtype=torch.float32, device=dev)
+        _lib.check(lib.gn_distmult_dense_scale(z.data_ptr(), ldz, n, d, w.data_ptr(), r, zw.data_ptr(), _stream()),
+                   "gn_distmult_dense_scale")
+        s = torch.empty((r, n, n), dtype=torch.float32, device=dev)
+        sgemm(False, True, n, n, d, zw.data_ptr(), d, z.data_ptr(), ldz, s.data_ptr(), n, dev, batch=r, sa=n * d, sb=0,
+              sc=n * n)
+        outs = []
+        for idx in (pi, ni):
+            out = torch.empty(e, dtype=torch.float32, device=dev)
+            _lib.check(lib.gn_distmult_dense_scores(s.data_ptr(), n, _ptr(idx[0]) if e else None,
+                                                    _ptr(idx[1]) if e else None, _ptr(et) if e else None, e,
+                                                    int(sigmoid), _ptr(out), _stream()), "gn_distmult_dense_scores")
+            outs.append(out)
+        ctx.sigmoid = bool(sigmoid)
+        ctx.keys = (pos_index, neg_index, edge_type)
+        ctx.save_for_backward(z, w, outs[0], outs[1])
+        return outs[0], outs[1]
+
+    @staticmethod
+    def backward(ctx, g_pos, g_neg):
+        from .graph import edge_struct
+        lib = _lib.load()
+        z, w, pos, neg = ctx.saved_tensors
+        pos_key, neg_key, et_key = ctx.keys
+        n, d, r = z.size(0), z.size(1), w.size(0)
+        dev, ldz = z.device, (z.stride(0) if z.size(0) > 1 else z.size(1))
+        c = torch.empty((r, n, n), dtype=torch.float32, device=dev)
+        for first, (key, g, out) in enumerate(((pos_key, g_pos, pos), (neg_key, g_neg, neg))):
+            coef = _distmult_coef(g.contiguous(), out, ctx.sigmoid)
+            es = edge_struct(key, et_key, n, r)
+            _lib.check(lib.gn_distmult_dense_coef(_ptr(es.node.rowptr), _ptr(es.ent_other), _ptr(es.ent_rel),
+                                                  _ptr(es.ent_eid), _ptr(coef), n, r, int(first == 0), c.data_ptr(),
+                                                  _stream()), "gn_distmult_dense_coef")
+        t = torch.empty((r, n, d), dtype=torch.float32, device=dev)
+        sgemm(False, False, n, d, n, c.data_ptr(), n, z.data_ptr(), ldz, t.data_ptr(), d, dev, batch=r, sa=n * n, sb=0,
+              sc=n * d)
+        dz = torch.empty((n, d), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.gn_distmult_dense_grads(t.data_ptr(), n, d, r, z.data_ptr(), ldz, w.data_ptr(), _ptr(dz), d,
+                                               _ptr(dw), _stream()), "gn_distmult_dense_grads")
+        return dz, dw, None, None, None, None
+
+
+# ----------------------------------------------------------------------------
 # multi-class decoder  softmax(z[node_list] W)   (decoder.py:38-45)
 # ----------------------------------------------------------------------------
 class MultiClass(torch.autograd.Function):

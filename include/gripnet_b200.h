@@ -228,6 +228,26 @@ int gn_distmult_bwd_w_resident(const gn_csr* rel_csr, const int32_t* rel_eid, co
                                const int64_t* dst, const float* coef, const float* z, int64_t ldz, int32_t n_nodes,
                                int32_t D, float* dw, float* partial, void* stream);
 
+/* K9/K10 in DENSE-RELATION form — EXPERIMENTAL (written at the end of round 1, not yet run on hardware, off by
+ * default).  For a small task supervertex with dense relation slices (pose: 645 nodes, 6 % of the node pairs per
+ * relation) the decoder is R batched dense products plus one 4-byte gather per edge instead of row gathers:
+ *   forward : zw[r] = z .* w[r] (gn_distmult_dense_scale), S[r] = zw[r] z^T (gn_sgemm, batch R),
+ *             score_e = act(S[rel_e][src_e][dst_e]) (gn_distmult_dense_scores)
+ *   backward: C[r][n][m] = sum of coef_e over the edges of relation r joining n and m, accumulated from the
+ *             endpoint CSR in entry order by one warp per node row (gn_distmult_dense_coef; zero_first clears C,
+ *             a second call adds another edge list), T[r] = C[r] z (gn_sgemm, batch R),
+ *             dz = sum_r T[r] .* w[r], dw[r] = 1/2 sum_n z[n] .* T[r][n] (gn_distmult_dense_grads).
+ * zw, T: [n_rel][n_nodes][D]; S, C: [n_rel][n_nodes][n_nodes]; all dense fp32, caller-owned. */
+int gn_distmult_dense_scale(const float* z, int64_t ldz, int32_t n_nodes, int32_t D, const float* w,
+                            int32_t n_rel, float* zw, void* stream);
+int gn_distmult_dense_scores(const float* S, int32_t n_nodes, const int64_t* src, const int64_t* dst,
+                             const int64_t* etype, int64_t n_edges, int sigmoid, float* out, void* stream);
+int gn_distmult_dense_coef(const int32_t* node_rowptr, const int32_t* ent_other, const int32_t* ent_rel,
+                           const int32_t* ent_eid, const float* coef, int32_t n_nodes, int32_t n_rel,
+                           int zero_first, float* C, void* stream);
+int gn_distmult_dense_grads(const float* T, int32_t n_nodes, int32_t D, int32_t n_rel, const float* z, int64_t ldz,
+                            const float* w, float* dz, int64_t lddz, float* dw, void* stream);
+
 /* ---- K11: multi-class decoder pieces  ------------------------------------ */
 /* row softmax over C columns (gripnet/decoder.py:43) and its backward */
 int gn_softmax_fwd(const float* logits, int64_t n, int32_t C, float* out, void* stream);

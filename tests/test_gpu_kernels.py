@@ -299,3 +299,40 @@ def test_losses_and_elementwise():
     r = torch.empty(33, 20, device=d)
     ops.relu_bwd(ops.M(a), ops.M(y), ops.M(r))
     assert torch.equal(r, torch.where(y > 0, a, torch.zeros_like(a)))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("GRIPNET_B200_TEST_DENSE") != "1",
+                    reason="experimental dense-relation decoder (csrc/decoder_dense.cu): opt-in with "
+                           "GRIPNET_B200_TEST_DENSE=1 until it has been run on hardware")
+@pytest.mark.parametrize("n,D,r,e", [(40, 20, 3, 900), (645, 80, 16, 400_000), (7, 8, 2, 300)])
+def test_distmult_dense_pair_matches_float64_and_the_gather_path(n, D, r, e, monkeypatch):
+    from gripnet_b200 import ops
+    from gripnet_b200.decoder import multiRelaInnerProductDecoder
+    rs = np.random.RandomState(n)
+    d = _dev()
+    z = torch.randn(n, D, dtype=torch.float64) * 0.3
+    w = torch.randn(r, D, dtype=torch.float64)
+    ei = torch.from_numpy(rs.randint(0, n, (2, e)))          # duplicates and self-loops included
+    ni = torch.from_numpy(rs.randint(0, n, (2, e)))
+    et = torch.from_numpy(np.sort(rs.randint(0, r, e)))
+    zr, wr = z.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    pos_ref = torch.sigmoid((zr[ei[0]] * zr[ei[1]] * wr[et]).sum(1))
+    neg_ref = torch.sigmoid((zr[ni[0]] * zr[ni[1]] * wr[et]).sum(1))
+    gp = torch.linspace(-1, 1, e, dtype=torch.float64)
+    gn = torch.linspace(0.5, -0.5, e, dtype=torch.float64)
+    ((pos_ref * gp).sum() + (neg_ref * gn).sum()).backward()
+    dec = multiRelaInnerProductDecoder(D, r).to(d)
+    res = []
+    for path in ("dense", "global"):
+        monkeypatch.setattr(ops, "DECODER_PATH", path)
+        with torch.no_grad():
+            dec.weight.copy_(w.float())
+        dec.weight.grad = None
+        zc = z.float().to(d).requires_grad_(True)
+        pos, neg = dec.score_pair(zc, ei.to(d), ni.to(d), et.to(d))
+        ((pos * gp.float().to(d)).sum() + (neg * gn.float().to(d)).sum()).backward()
+        assert rel_err(pos, pos_ref) < TOL and rel_err(neg, neg_ref) < TOL, path
+        assert rel_err(zc.grad, zr.grad) < TOL and rel_err(dec.weight.grad, wr.grad) < TOL, path
+        res.append((pos.detach().clone(), zc.grad.clone()))
+    again = dec.score_pair(z.float().to(d), ei.to(d), ni.to(d), et.to(d))[0]     # "global" again: deterministic
+    assert torch.equal(again, res[1][0])
