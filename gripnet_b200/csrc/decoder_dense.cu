@@ -1,5 +1,6 @@
-// K9/K10, dense-relation form — EXPERIMENTAL: written at the end of round 1, NOT YET RUN ON HARDWARE, off by
-// default (ops.DECODER_PATH == "dense" selects it; its GPU test is opt-in).  DESIGN.md §9a has the reasoning.
+// K9/K10, dense-relation form — EXPERIMENTAL: parity-checked on a B200 at the end of round 1 (3 shapes incl.
+// pose-0 size, profiles/r01_v16_dense_decoder_pytest.txt) but NOT YET TIMED, so off by default
+// (ops.DECODER_PATH == "dense" selects it).  DESIGN.md §9a has the reasoning.
 //
 // The link decoder of the pose family scores edges inside a SMALL task supervertex (645 drugs) whose relation
 // slices are dense: 25 k edges per relation = 6 % of the 645^2 node pairs.  Then, per relation r,

@@ -707,7 +707,7 @@ class DistMultPair(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------
-# dense-relation decoder — EXPERIMENTAL (not yet run on hardware; GRIPNET_B200_DECODER=dense selects it)
+# dense-relation decoder — EXPERIMENTAL (parity-checked on a B200, not yet timed; GRIPNET_B200_DECODER=dense)
 # ----------------------------------------------------------------------------
 _DENSE_MAX_BYTES = 512 << 20          # S and C are [R, n, n] fp32 each
 

@@ -228,8 +228,7 @@ int gn_distmult_bwd_w_resident(const gn_csr* rel_csr, const int32_t* rel_eid, co
                                const int64_t* dst, const float* coef, const float* z, int64_t ldz, int32_t n_nodes,
                                int32_t D, float* dw, float* partial, void* stream);
 
-/* K9/K10 in DENSE-RELATION form — EXPERIMENTAL (written at the end of round 1, not yet run on hardware, off by
- * default).  For a small task supervertex with dense relation slices (pose: 645 nodes, 6 % of the node pairs per
+/* K9/K10 in DENSE-RELATION form — EXPERIMENTAL (parity-checked on a B200, not yet timed, off by default).  For a small task supervertex with dense relation slices (pose: 645 nodes, 6 % of the node pairs per
  * relation) the decoder is R batched dense products plus one 4-byte gather per edge instead of row gathers:
  *   forward : zw[r] = z .* w[r] (gn_distmult_dense_scale), S[r] = zw[r] z^T (gn_sgemm, batch R),
  *             score_e = act(S[rel_e][src_e][dst_e]) (gn_distmult_dense_scores)

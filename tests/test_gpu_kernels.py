@@ -301,11 +301,10 @@ def test_losses_and_elementwise():
     assert torch.equal(r, torch.where(y > 0, a, torch.zeros_like(a)))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GRIPNET_B200_TEST_DENSE") != "1",
-                    reason="experimental dense-relation decoder (csrc/decoder_dense.cu): opt-in with "
-                           "GRIPNET_B200_TEST_DENSE=1 until it has been run on hardware")
 @pytest.mark.parametrize("n,D,r,e", [(40, 20, 3, 900), (645, 80, 16, 400_000), (7, 8, 2, 300)])
 def test_distmult_dense_pair_matches_float64_and_the_gather_path(n, D, r, e, monkeypatch):
+    """Dense-relation decoder (csrc/decoder_dense.cu, GRIPNET_B200_DECODER=dense; not the default path): same
+    scores and gradients as the float64 evaluation and as the gather-multiply-reduce kernels."""
     from gripnet_b200 import ops
     from gripnet_b200.decoder import multiRelaInnerProductDecoder
     rs = np.random.RandomState(n)
