@@ -31,6 +31,16 @@ class GnAdamTensor(C.Structure):
                 ("n", C.c_int64)]
 
 
+class GnPeerSegment(C.Structure):
+    """Mirror of ``gn_peer_segment``."""
+    _fields_ = [("src", C.c_void_p), ("bytes", C.c_int64), ("slot_offset", C.c_int64), ("peer", C.c_int32)]
+
+
+class GnSumSegment(C.Structure):
+    """Mirror of ``gn_sum_segment``."""
+    _fields_ = [("dst", C.c_void_p), ("n", C.c_int64), ("slot_offset", C.c_int64)]
+
+
 _P, _I32, _I64, _F, _SZ, _INT = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_int
 _CSR = C.POINTER(GnCsr)
 
@@ -38,6 +48,8 @@ _CSR = C.POINTER(GnCsr)
 SIGNATURES = {
     "gn_version": (_INT, []),
     "gn_error_string": (C.c_char_p, [_INT]),
+    "gn_last_cuda_error": (_INT, []),
+    "gn_last_cuda_error_string": (C.c_char_p, []),
     "gn_launch_count": (C.c_uint64, []),
     "gn_csr_from_keys_workspace_bytes": (_SZ, [_I64, _I32]),
     "gn_csr_from_keys": (_INT, [_P, _I64, _I32, _P, _P, _P, _SZ, _P]),
@@ -47,6 +59,11 @@ SIGNATURES = {
     "gn_gcn_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "gn_gcn_prep": (_INT, [_P, _P, _P, _I64, _I32, _I32, _INT, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                            _P, _P, _P, _P, _SZ, _P]),
+    "gn_edge_filter_workspace_bytes": (_SZ, [_I64]),
+    "gn_edge_filter": (_INT, [_P, _P, _P, _I64, _INT, _I64, _I64, _P, _P, _P, _P, _I64, _P, _P, _SZ, _P]),
+    "gn_gcn_part_workspace_bytes": (_SZ, [_I64, _I32]),
+    "gn_gcn_part_structure": (_INT, [_P, _P, _P, _I64, _I32, _I32, _INT, _F, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gn_gcn_part_values": (_INT, [_P, _P, _I32, _I32, _P, _P, _INT, _P, _P]),
     "gn_rgcn_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "gn_rgcn_prep": (_INT, [_P, _P, _I64, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gn_edge_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
@@ -59,24 +76,23 @@ SIGNATURES = {
                         _F, _INT, _P, _I64, _P, _I64, _P, _I32, _P, _SZ, _P]),
     "gn_tc_gemm_workspace_bytes": (_SZ, [_I32, _I32, _I32]),
     "gn_tc_gemm": (_INT, [_INT, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _SZ, _P]),
+    "gn_tc_gemm_rel_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
+    "gn_tc_gemm_rel": (_INT, [_I32, _I32, _I32, _I32, _P, _I64, _P, _P, _I64, _P, _SZ, _P]),
     "gn_distmult_fwd": (_INT, [_P, _I64, _I32, _P, _P, _P, _P, _I64, _INT, _P, _P]),
     "gn_distmult_coef": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "gn_distmult_bwd_z": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I64, _P, _P]),
     "gn_distmult_bwd_w": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
-    "gn_distmult_resident_ok": (_INT, [_I64, _I32, _I64]),
-    "gn_distmult_fwd_resident": (_INT, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _I64, _INT, _P, _P]),
-    "gn_distmult_bwd_z_resident": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I64, _P, _P]),
-    "gn_distmult_bwd_w_resident": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
-    "gn_distmult_dense_scale": (_INT, [_P, _I64, _I32, _I32, _P, _I32, _P, _P]),
-    "gn_distmult_dense_scores": (_INT, [_P, _I32, _P, _P, _P, _I64, _INT, _P, _P]),
-    "gn_distmult_dense_coef": (_INT, [_P, _P, _P, _P, _P, _I32, _I32, _INT, _P, _P]),
-    "gn_distmult_dense_grads": (_INT, [_P, _I32, _I32, _I32, _P, _I64, _P, _P, _I64, _P, _P]),
+    "gn_pair_prep_workspace_bytes": (_SZ, [_I64]),
+    "gn_pair_prep": (_INT, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "gn_distmult_bwd_pairs": (_INT, [_CSR, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
+    "gn_distmult_grads": (_INT, [_P, _P, _I32, _I32, _I32, _P, _I64, _P, _P, _I64, _P, _P]),
     "gn_softmax_fwd": (_INT, [_P, _I64, _I32, _P, _P]),
     "gn_softmax_bwd": (_INT, [_P, _P, _I64, _I32, _P, _P]),
     "gn_map2d": (_INT, [_INT, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "gn_relu_bwd": (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "gn_abs_bwd": (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _F, _P]),
     "gn_axpby": (_INT, [_P, _I64, _F, _P, _I64, _F, _P, _I64, _I64, _I32, _P]),
+    "gn_mean3": (_INT, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "gn_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
     "gn_colsum": (_INT, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),
     "gn_loss_workspace_bytes": (_SZ, [_I64]),
@@ -96,8 +112,12 @@ SIGNATURES = {
     "gn_nc_metrics": (_INT, [_P, _P, _I64, _I32, _P, _P, _SZ, _P]),
     "gn_peer_max_world": (_INT, []),
     "gn_peer_allgather": (_INT, [_P, _I32, _I32, _I64, _I64, _I64, _I32, _P, _P, _P, _P]),
+    "gn_peer_max_segments": (_INT, []),
+    "gn_peer_push": (_INT, [_P, _I32, _I32, _I64, _I64, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
+    "gn_slot_sum": (_INT, [_P, _I32, _I64, _P, _I32, _P]),
 }
 
+GN_ERR_CUDA = -4
 EW_COPY, EW_ABS, EW_RELU, EW_ADD = 0, 1, 2, 3
 CSR_ROW_IS_CHUNK = 1
 
@@ -128,6 +148,8 @@ def load():
 def check(status, what=""):
     if status != 0:
         msg = load().gn_error_string(status).decode()
+        if status == GN_ERR_CUDA and load().gn_last_cuda_error() != 0:
+            msg += " [cuda: %s]" % load().gn_last_cuda_error_string().decode()
         raise RuntimeError(f"gripnet_b200: {what or 'call'} failed: {msg} (status {status})")
 
 

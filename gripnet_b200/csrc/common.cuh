@@ -10,6 +10,9 @@
 namespace gn {
 
 extern std::atomic<uint64_t> g_launches;
+// cudaError_t of the most recent failed launch / runtime call made by this library (0 = none); reported by
+// gn_last_cuda_error() so the host side can show the real CUDA error string next to GN_ERR_CUDA
+extern std::atomic<int> g_last_cuda_error;
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -21,8 +24,9 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
   do {                                                                          \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                 \
     gn::g_launches.fetch_add(1, std::memory_order_relaxed);                     \
-    if (cudaPeekAtLastError() != cudaSuccess) {                                 \
-      (void)cudaGetLastError();                                                 \
+    const cudaError_t _gn_e = cudaGetLastError(); /* status of THIS launch */   \
+    if (_gn_e != cudaSuccess) {                                                 \
+      gn::g_last_cuda_error.store(int(_gn_e), std::memory_order_relaxed);       \
       return GN_ERR_CUDA;                                                       \
     }                                                                           \
   } while (0)

@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "rowsplit.cuh"
+#include "sortkit.cuh"
 
 namespace gn {
 
@@ -196,6 +197,131 @@ __global__ void __launch_bounds__(256) distmult_bwd_kernel(const gn_csr csr, con
 }
 
 // ---------------------------------------------------------------------------
+// backward in ONE gather pass (K10).  The endpoint entries of an edge list are grouped by (node, relation)
+// — the "pair CSR", rows = node * n_rel + rel — and one walk forms
+//     T[n, r, :] = sum over the entries (other, e) of pair row (n, r) of coef[e] * z[other, :].
+// Both gradients follow from T without touching the edges again:
+//     dz[n]  = sum_r T[n, r] .* w[r]
+//     dw[r]  = 1/2 sum_n z[n] .* T[n, r]          (every edge sits in two pair rows: (src, r) and (dst, r))
+// so the second gather pass of the two-walk scheme (z[src] and z[dst] per edge for dw) disappears, and the
+// walk itself carries no relation logic (no w gather, no run accumulator): fewer registers, more warps.
+// Positive and negative lists write their own T; distmult_grads_kernel adds them on the fly.
+// ---------------------------------------------------------------------------
+template <int LPE, int VEC, int NV>
+__global__ void __launch_bounds__(256) pair_walk_kernel(const gn_csr csr, const int32_t* __restrict__ ent_other,
+                                                        const int32_t* __restrict__ ent_eid,
+                                                        const float* __restrict__ coef, const float* __restrict__ z,
+                                                        int64_t ldz, int D, float* __restrict__ T,
+                                                        float* __restrict__ partial) {
+  ChunkInfo ci;
+  if (!chunk_info(csr, ci)) return;
+  constexpr int EPI = 32 / LPE;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane / LPE, fl = lane % LPE;
+  Vec<VEC> acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[v].v[i] = 0.f;
+  for (int s0 = ci.beg + slot; s0 < ci.end; s0 += 2 * EPI) {
+    const int s1 = s0 + EPI;
+    const bool has1 = s1 < ci.end;
+    const float* pa0 = z + int64_t(__ldg(ent_other + s0)) * ldz;
+    const float* pa1 = has1 ? z + int64_t(__ldg(ent_other + s1)) * ldz : z;
+    const float g0 = __ldg(coef + __ldg(ent_eid + s0));
+    const float g1 = has1 ? __ldg(coef + __ldg(ent_eid + s1)) : 0.f;
+    Vec<VEC> a0[NV], a1[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int f = (v * LPE + fl) * VEC;
+      if (f < D) {
+        a0[v] = load_vec<VEC>(pa0 + f);
+        a1[v] = load_vec<VEC>(pa1 + f);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int f = (v * LPE + fl) * VEC;
+      if (f < D) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          acc[v].v[i] = fmaf(g0, a0[v].v[i], acc[v].v[i]);
+          acc[v].v[i] = fmaf(g1, a1[v].v[i], acc[v].v[i]);     // g1 == 0 when the slot has no 2nd entry
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) reduce_slots<LPE, VEC>(acc[v]);
+  const int row = ci.row;
+  auto emit = [&](int, int f, const Vec<VEC>& sum) { store_vec<VEC>(T + int64_t(row) * D + f, sum); };
+  finish_row<LPE, VEC, NV>(csr, ci, acc, D, partial, emit);
+}
+
+// dz / dw from T (and an optional second T of another edge list).  One CTA per output row: blocks
+// [0, n_nodes) form dz[n] = sum_r T[n,r] .* w[r], blocks [n_nodes, n_nodes + n_rel) form
+// dw[r] = 1/2 sum_n z[n] .* T[n,r].  The CTA's threads are G groups of D columns; group g adds the terms
+// i = g, g + G, ... in order, then the G partial rows are added in group order: a fixed summation order.
+constexpr int kGradThreads = 1024;
+__global__ void __launch_bounds__(kGradThreads) distmult_grads_kernel(const float* __restrict__ T,
+                                                                     const float* __restrict__ T2, int n_nodes,
+                                                                     int n_rel, int D, const float* __restrict__ z,
+                                                                     int64_t ldz, const float* __restrict__ w,
+                                                                     float* __restrict__ dz, int64_t lddz,
+                                                                     float* __restrict__ dw) {
+  extern __shared__ float red[];                       // [G][D]
+  const int G = kGradThreads / D > 0 ? kGradThreads / D : 1;
+  const bool is_dz = int(blockIdx.x) < n_nodes;
+  const int row = is_dz ? int(blockIdx.x) : int(blockIdx.x) - n_nodes;
+  const int n_terms = is_dz ? n_rel : n_nodes;
+  if (is_dz ? dz == nullptr : dw == nullptr) return;
+  for (int f0 = 0; f0 < D; f0 += kGradThreads) {       // D > 1024: column panels (G == 1)
+    const int g = D <= kGradThreads ? int(threadIdx.x) / D : 0;
+    const int f = D <= kGradThreads ? int(threadIdx.x) % D : f0 + int(threadIdx.x);
+    float acc = 0.f;
+    if (g < G && f < D) {
+      for (int i = g; i < n_terms; i += G) {
+        const int64_t t = is_dz ? (int64_t(row) * n_rel + i) * D + f : (int64_t(i) * n_rel + row) * D + f;
+        float tv = __ldg(T + t);
+        if (T2) tv += __ldg(T2 + t);
+        const float o = is_dz ? __ldg(w + int64_t(i) * D + f) : __ldg(z + int64_t(i) * ldz + f);
+        acc = fmaf(tv, o, acc);
+      }
+      red[g * D + (f - f0)] = acc;
+    }
+    __syncthreads();
+    if (g == 0 && f < D) {
+      float s = red[f - f0];
+      for (int k = 1; k < G; ++k) s += red[k * D + (f - f0)];
+      if (is_dz) dz[int64_t(row) * lddz + f] = s;
+      else dw[int64_t(row) * D + f] = 0.5f * s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void pair_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                 const int64_t* __restrict__ etype, int64_t n_edges, int32_t n_rel,
+                                 int32_t* __restrict__ key) {
+  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int r = int32_t(etype[e]);
+  key[e] = int32_t(src[e]) * n_rel + r;
+  key[n_edges + e] = int32_t(dst[e]) * n_rel + r;
+}
+
+__global__ void pair_fill_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t n_edges,
+                                 const int32_t* __restrict__ perm, int32_t* __restrict__ ent_other,
+                                 int32_t* __restrict__ ent_eid) {
+  const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= 2 * n_edges) return;
+  const int64_t q = perm[s];
+  const int64_t e = q < n_edges ? q : q - n_edges;
+  ent_other[s] = int32_t(q < n_edges ? dst[e] : src[e]);
+  ent_eid[s] = int32_t(e);
+}
+
+// ---------------------------------------------------------------------------
 // softmax (warp per row)
 // ---------------------------------------------------------------------------
 __global__ void softmax_fwd_kernel(const float* __restrict__ x, int64_t n, int C, float* __restrict__ y) {
@@ -367,6 +493,79 @@ int gn_softmax_bwd(const float* out, const float* grad_out, int64_t n, int32_t C
   if (!out || !grad_out || !grad_logits) return GN_ERR_ARG;
   GN_LAUNCH(softmax_bwd_kernel, (unsigned)ceil_div(n * 32, 256), 256, 0, as_stream(stream), out, grad_out, n, C,
             grad_logits);
+  return GN_OK;
+}
+
+size_t gn_pair_prep_workspace_bytes(int64_t n_edges) {
+  const size_t E2 = size_t(n_edges > 0 ? 2 * n_edges : 1);
+  return 3 * align_up(E2 * 4) + sort_ws_bytes(2 * n_edges) + 4096;
+}
+
+int gn_pair_prep(const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges, int32_t n_nodes,
+                 int32_t n_rel, int32_t* pair_rowptr, int32_t* ent_other, int32_t* ent_eid, void* ws, size_t ws_bytes,
+                 void* stream) {
+  if (n_edges < 0 || n_nodes <= 0 || n_rel <= 0 || !pair_rowptr) return GN_ERR_ARG;
+  if (n_edges > 0 && (!src || !dst || !etype || !ent_other || !ent_eid)) return GN_ERR_ARG;
+  if (2 * n_edges >= (int64_t(1) << 31) || int64_t(n_nodes) * n_rel >= (int64_t(1) << 31)) return GN_ERR_RANGE;
+  cudaStream_t st = as_stream(stream);
+  const int32_t n_rows = n_nodes * n_rel;
+  const int64_t E2 = 2 * n_edges;
+  const size_t Ea = size_t(E2 > 0 ? E2 : 1);
+  Arena a(ws, ws_bytes);
+  int32_t* key = a.take<int32_t>(Ea);
+  int32_t* sorted = a.take<int32_t>(Ea);
+  int32_t* perm = a.take<int32_t>(Ea);
+  if (!a.ok()) return GN_ERR_WORKSPACE;
+  if (n_edges > 0) {
+    GN_LAUNCH(pair_keys_kernel, (unsigned)ceil_div(n_edges, 256), 256, 0, st, src, dst, etype, n_edges, n_rel, key);
+  }
+  GN_CHECK(sort_pairs(key, nullptr, sorted, perm, E2, bits_for(n_rows > 1 ? n_rows : 2), a.base + a.off,
+                      a.cap - a.off, st));
+  GN_CHECK(rowptr_from_sorted(sorted, E2, n_rows, pair_rowptr, st));
+  if (n_edges > 0) {
+    GN_LAUNCH(pair_fill_kernel, (unsigned)ceil_div(E2, 256), 256, 0, st, src, dst, n_edges, (const int32_t*)perm,
+              ent_other, ent_eid);
+  }
+  return GN_OK;
+}
+
+int gn_distmult_bwd_pairs(const gn_csr* pair_csr, const int32_t* ent_other, const int32_t* ent_eid, const float* coef,
+                          const float* z, int64_t ldz, int32_t D, float* T, float* partial, void* stream) {
+  if (!pair_csr || !z || !T || D <= 0) return GN_ERR_ARG;
+  if (pair_csr->nnz > 0 && (!ent_other || !ent_eid || !coef)) return GN_ERR_ARG;
+  const gn_csr& csr = *pair_csr;
+  if (csr.n_rows == 0 || csr.n_chunks == 0) return GN_OK;
+  if (csr.n_chunks > csr.n_rows && !partial) return GN_ERR_ARG;
+  const bool v4 = (D % 4 == 0) && (ldz % 4 == 0) && aligned16(z) && aligned16(T) && (!partial || aligned16(partial));
+  const WidthPlan p = plan_width(D, v4, true);
+  if (!p.ok) return GN_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
+#define GN_PW_CASE(L, V, N)                                                                                  \
+  if (p.lpe == L && p.vec == V && p.nv == N) {                                                               \
+    GN_LAUNCH((pair_walk_kernel<L, V, N>), grid, 256, 0, st, csr, ent_other, ent_eid, coef, z, ldz, D, T,    \
+              partial);                                                                                      \
+    return GN_OK;                                                                                            \
+  }
+#define GN_PW_CASES(L, V) GN_PW_CASE(L, V, 1) GN_PW_CASE(L, V, 2) GN_PW_CASE(L, V, 4) GN_PW_CASE(L, V, 5) \
+  GN_PW_CASE(L, V, 8)
+  GN_PW_CASES(4, 4)
+  GN_PW_CASE(8, 4, 3)
+  GN_PW_CASES(32, 4)
+  GN_PW_CASES(4, 1)
+  GN_PW_CASES(32, 1)
+#undef GN_PW_CASES
+#undef GN_PW_CASE
+  return GN_ERR_ARG;
+}
+
+int gn_distmult_grads(const float* T, const float* T2, int32_t n_nodes, int32_t n_rel, int32_t D, const float* z,
+                      int64_t ldz, const float* w, float* dz, int64_t lddz, float* dw, void* stream) {
+  if (n_nodes <= 0 || n_rel <= 0 || D <= 0 || !T || !z || !w || (!dz && !dw)) return GN_ERR_ARG;
+  const int G = kGradThreads / D > 0 ? kGradThreads / D : 1;
+  const size_t smem = size_t(G) * size_t(D < kGradThreads ? D : kGradThreads) * sizeof(float);
+  GN_LAUNCH(distmult_grads_kernel, (unsigned)(n_nodes + n_rel), kGradThreads, smem, as_stream(stream), T, T2, n_nodes,
+            n_rel, D, z, ldz, w, dz, lddz, dw);
   return GN_OK;
 }
 

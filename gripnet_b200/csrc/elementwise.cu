@@ -72,6 +72,18 @@ __global__ void axpby_kernel(const float* __restrict__ a, int64_t lda, float alp
   dst[r * ldd + c] = v;
 }
 
+// ((a + b) + c) / 3 in the reference's evaluation order and with a true division (GripNet-freebase-d.py:160-161)
+__global__ void mean3_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                             const float* __restrict__ c, int64_t ldc, float* __restrict__ dst, int64_t ldd, int64_t n,
+                             int F) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n * F) return;
+  const int64_t r = idx / F;
+  const int col = int(idx - r * F);
+  const float v = __fadd_rn(__fadd_rn(a[r * lda + col], b[r * ldb + col]), c[r * ldc + col]);
+  dst[r * ldd + col] = __fdiv_rn(v, 3.0f);
+}
+
 // ---- column sums: block b sums rows [b*rows_per_block, ...) -> ws[b, F]; then a
 // second kernel adds the block rows in order.
 constexpr int kColsumThreads = 256;
@@ -270,6 +282,16 @@ int gn_axpby(const float* a, int64_t lda, float alpha, const float* b, int64_t l
   if (!a || !dst) return GN_ERR_ARG;
   GN_LAUNCH(axpby_kernel, (unsigned)ceil_div(n * F, 256), 256, 0, as_stream(stream), a, lda, alpha, b, ldb, beta, dst,
             ldd, n, F);
+  return GN_OK;
+}
+
+int gn_mean3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* dst,
+             int64_t ldd, int64_t n, int32_t F, void* stream) {
+  if (n < 0 || F <= 0) return GN_ERR_ARG;
+  if (n == 0) return GN_OK;
+  if (!a || !b || !c || !dst) return GN_ERR_ARG;
+  GN_LAUNCH(mean3_kernel, (unsigned)ceil_div(n * F, 256), 256, 0, as_stream(stream), a, lda, b, ldb, c, ldc, dst, ldd,
+            n, F);
   return GN_OK;
 }
 

@@ -43,19 +43,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(256) peer_allgather_kernel(const PeerArgs a) {
-  const int64_t n16 = a.slot_bytes >> 4;
-  const int64_t slot_off = int64_t(a.rank) * a.slot_bytes;
-  const int4* __restrict__ src = reinterpret_cast<const int4*>(a.buf[a.rank] + slot_off);
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
-    const int4 v = src[i];
-#pragma unroll 1
-    for (int s = 1; s < a.world; ++s) {
-      const int peer = (a.rank + s) % a.world;
-      reinterpret_cast<int4*>(a.buf[peer] + slot_off)[i] = v;
-    }
-  }
+// Every CTA has issued its stores: the LAST CTA publishes "rank r has delivered buffer b, use e" in every
+// peer's flag block and waits until every peer has published the same for this rank.
+__device__ __forceinline__ void signal_and_wait(const PeerArgs& a) {
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x != 0) return;
@@ -83,6 +73,131 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(const PeerArgs a) {
       if (++spins > (1u << 23)) {
         *reinterpret_cast<volatile unsigned int*>(a.abort_flag) = 1;
         return;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_allgather_kernel(const PeerArgs a) {
+  const int64_t n16 = a.slot_bytes >> 4;
+  const int64_t slot_off = int64_t(a.rank) * a.slot_bytes;
+  const int4* __restrict__ src = reinterpret_cast<const int4*>(a.buf[a.rank] + slot_off);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const int4 v = src[i];
+#pragma unroll 1
+    for (int s = 1; s < a.world; ++s) {
+      const int peer = (a.rank + s) % a.world;
+      reinterpret_cast<int4*>(a.buf[peer] + slot_off)[i] = v;
+    }
+  }
+  signal_and_wait(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segmented push + rank-ordered sum: the small reductions of a partitioned step without NCCL.
+//   gn_peer_push : every segment (src pointer, bytes, offset inside a slot, target peer or ALL) is stored
+//                  into slot `rank` of the exchange buffer of its target rank(s) — own arena included —
+//                  then the same publish / wait protocol as the slot all-gather.  With one segment per
+//                  peer this is an all-to-all (the reduce-scatter of the decoder's dz); with every
+//                  segment sent to ALL it is the all-gather phase of an all-reduce (bucketed weight
+//                  gradients + the loss share).
+//   gn_slot_sum  : dst[i] = slot_0[i] + slot_1[i] + ... + slot_{world-1}[i], in RANK ORDER: every rank
+//                  adds the same numbers in the same order, so replicated results are bit-identical on all
+//                  ranks and run to run (NCCL's ring / tree order is neither specified nor rank-symmetric).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxSegments = 40;
+constexpr int kPushBlockBytes = 256 * 16 * 4;   // 16 KB of a segment per CTA
+
+struct PushBatch {
+  const char* src[kMaxSegments];
+  int64_t bytes[kMaxSegments];
+  int64_t slot_off[kMaxSegments];
+  int32_t peer[kMaxSegments];                 // -1: every rank
+  int32_t block_first[kMaxSegments + 1];
+  int32_t n_segs;
+};
+
+__global__ void __launch_bounds__(256) peer_push_kernel(const PeerArgs a, const PushBatch b) {
+  __shared__ int s_seg;
+  if (threadIdx.x == 0) {
+    int s = 0;
+    while (s + 1 < b.n_segs && int(blockIdx.x) >= b.block_first[s + 1]) ++s;
+    s_seg = s;
+  }
+  __syncthreads();
+  const int s = s_seg;
+  const int64_t base = int64_t(int(blockIdx.x) - b.block_first[s]) * kPushBlockBytes;
+  const int64_t bytes = b.bytes[s];
+  const char* __restrict__ src = b.src[s];
+  const int64_t dst_off = int64_t(a.rank) * a.slot_bytes + b.slot_off[s];
+  const int p_first = b.peer[s] < 0 ? 0 : b.peer[s];
+  const int p_last = b.peer[s] < 0 ? a.world - 1 : b.peer[s];
+  const bool v16 = ((reinterpret_cast<uintptr_t>(src) | uintptr_t(bytes) | uintptr_t(dst_off)) & 15) == 0;
+  if (v16) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int64_t i = base + (int64_t(it) * 256 + threadIdx.x) * 16;
+      if (i >= bytes) break;
+      const int4 v = *reinterpret_cast<const int4*>(src + i);
+      for (int q = p_first; q <= p_last; ++q) {
+        const int peer = (b.peer[s] < 0) ? (a.rank + q) % a.world : q;     // staggered start: not everyone hits rank 0 first
+        *reinterpret_cast<int4*>(a.buf[peer] + dst_off + i) = v;
+      }
+    }
+  } else {   // 4-byte granularity (the scalar loss share, odd-sized tensors)
+    const int64_t end = base + kPushBlockBytes < bytes ? base + kPushBlockBytes : bytes;
+    for (int64_t i = base + int64_t(threadIdx.x) * 4; i < end; i += 256 * 4) {
+      const int v = *reinterpret_cast<const int*>(src + i);
+      for (int q = p_first; q <= p_last; ++q) {
+        const int peer = (b.peer[s] < 0) ? (a.rank + q) % a.world : q;
+        *reinterpret_cast<int*>(a.buf[peer] + dst_off + i) = v;
+      }
+    }
+  }
+  signal_and_wait(a);
+}
+
+struct SumBatch {
+  float* dst[kMaxSegments];
+  int64_t n[kMaxSegments];
+  int64_t slot_off[kMaxSegments];             // bytes
+  int32_t block_first[kMaxSegments + 1];
+  int32_t n_segs;
+};
+constexpr int kSumBlockElems = 256 * 4 * 4;   // 4096 floats per CTA
+
+__global__ void __launch_bounds__(256) slot_sum_kernel(const char* __restrict__ buf, int world, int64_t slot_bytes,
+                                                       const SumBatch b) {
+  __shared__ int s_seg;
+  if (threadIdx.x == 0) {
+    int s = 0;
+    while (s + 1 < b.n_segs && int(blockIdx.x) >= b.block_first[s + 1]) ++s;
+    s_seg = s;
+  }
+  __syncthreads();
+  const int s = s_seg;
+  const int64_t n = b.n[s];
+  float* __restrict__ dst = b.dst[s];
+  const char* __restrict__ src0 = buf + b.slot_off[s];
+  const int64_t base = int64_t(int(blockIdx.x) - b.block_first[s]) * kSumBlockElems;
+  const bool v16 = ((reinterpret_cast<uintptr_t>(dst) | uintptr_t(b.slot_off[s]) | uintptr_t(slot_bytes)) & 15) == 0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int64_t i = base + (int64_t(it) * 256 + threadIdx.x) * 4;
+    if (i >= n) break;
+    if (v16 && i + 4 <= n) {
+      float4 acc = *reinterpret_cast<const float4*>(src0 + i * 4);
+      for (int p = 1; p < world; ++p) {
+        const float4 v = *reinterpret_cast<const float4*>(src0 + int64_t(p) * slot_bytes + i * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(dst + i) = acc;
+    } else {
+      for (int64_t j = i; j < n && j < i + 4; ++j) {
+        float acc = *reinterpret_cast<const float*>(src0 + j * 4);
+        for (int p = 1; p < world; ++p) acc += *reinterpret_cast<const float*>(src0 + int64_t(p) * slot_bytes + j * 4);
+        dst[j] = acc;
       }
     }
   }
@@ -118,5 +233,92 @@ extern "C" int gn_peer_allgather(const uint64_t* arena_base /*host*/, int32_t wo
   if (ctas > 148 * 2) ctas = 148 * 2;
   if (ctas < 1) ctas = 1;
   GN_LAUNCH(peer_allgather_kernel, (unsigned)ctas, 256, 0, as_stream(stream), a);
+  return GN_OK;
+}
+
+static int fill_peer_args(PeerArgs& a, const uint64_t* arena_base, int32_t world, int32_t rank, int64_t buf_offset,
+                          int64_t slot_bytes, int64_t flag_offset, int32_t flag_index, uint64_t* seq, uint32_t* done,
+                          uint32_t* abort_flag) {
+  if (!arena_base || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || slot_bytes < 0 || flag_index < 0 ||
+      !seq || !done || !abort_flag)
+    return GN_ERR_ARG;
+  if (slot_bytes % 16 != 0 || buf_offset % 16 != 0 || flag_offset % 8 != 0) return GN_ERR_ARG;
+  for (int p = 0; p < kMaxPeers; ++p) {
+    const uint64_t base = p < world ? arena_base[p] : 0;
+    if (p < world && base == 0) return GN_ERR_ARG;
+    a.buf[p] = reinterpret_cast<char*>(base + (p < world ? uint64_t(buf_offset) : 0));
+    a.flags[p] = reinterpret_cast<unsigned long long*>(base + (p < world ? uint64_t(flag_offset) : 0));
+  }
+  a.world = world; a.rank = rank; a.slot_bytes = slot_bytes; a.flag_index = flag_index;
+  a.seq = reinterpret_cast<unsigned long long*>(seq);
+  a.done = done;
+  a.abort_flag = abort_flag;
+  return GN_OK;
+}
+
+extern "C" int gn_peer_max_segments(void) { return kMaxSegments; }
+
+extern "C" int gn_peer_push(const uint64_t* arena_base /*host*/, int32_t world, int32_t rank, int64_t buf_offset,
+                            int64_t slot_bytes, const gn_peer_segment* segs /*host*/, int32_t n_segs,
+                            int64_t flag_offset, int32_t flag_index, uint64_t* seq, uint32_t* done,
+                            uint32_t* abort_flag, void* stream) {
+  PeerArgs a;
+  GN_CHECK(fill_peer_args(a, arena_base, world, rank, buf_offset, slot_bytes, flag_offset, flag_index, seq, done,
+                          abort_flag));
+  if (n_segs < 1 || n_segs > kMaxSegments || !segs) return GN_ERR_ARG;
+  PushBatch b;
+  int64_t blocks = 0;
+  b.n_segs = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const gn_peer_segment& g = segs[i];
+    if (g.bytes < 0 || g.bytes % 4 != 0 || g.slot_offset < 0 || g.slot_offset % 4 != 0 ||
+        g.slot_offset + g.bytes > slot_bytes || g.peer >= world)
+      return GN_ERR_ARG;
+    if (g.bytes == 0) continue;
+    if (!g.src) return GN_ERR_ARG;
+    const int k = b.n_segs++;
+    b.src[k] = static_cast<const char*>(g.src);
+    b.bytes[k] = g.bytes;
+    b.slot_off[k] = g.slot_offset;
+    b.peer[k] = g.peer < 0 ? -1 : g.peer;
+    b.block_first[k] = int32_t(blocks);
+    blocks += ceil_div(g.bytes, kPushBlockBytes);
+    if (blocks >= (int64_t(1) << 30)) return GN_ERR_RANGE;
+  }
+  if (b.n_segs == 0) {                      // nothing to send: still take part in the publish / wait round
+    b.n_segs = 1;
+    b.src[0] = nullptr; b.bytes[0] = 0; b.slot_off[0] = 0; b.peer[0] = rank; b.block_first[0] = 0;
+    blocks = 1;
+  }
+  b.block_first[b.n_segs] = int32_t(blocks);
+  GN_LAUNCH(peer_push_kernel, (unsigned)blocks, 256, 0, as_stream(stream), a, b);
+  return GN_OK;
+}
+
+extern "C" int gn_slot_sum(const void* buf, int32_t world, int64_t slot_bytes, const gn_sum_segment* segs /*host*/,
+                           int32_t n_segs, void* stream) {
+  if (!buf || world < 1 || slot_bytes < 0 || slot_bytes % 4 != 0 || n_segs < 0 || n_segs > kMaxSegments ||
+      (n_segs > 0 && !segs))
+    return GN_ERR_ARG;
+  SumBatch b;
+  int64_t blocks = 0;
+  b.n_segs = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const gn_sum_segment& g = segs[i];
+    if (g.n < 0 || g.slot_offset < 0 || g.slot_offset % 4 != 0 || g.slot_offset + g.n * 4 > slot_bytes) return GN_ERR_ARG;
+    if (g.n == 0) continue;
+    if (!g.dst) return GN_ERR_ARG;
+    const int k = b.n_segs++;
+    b.dst[k] = g.dst;
+    b.n[k] = g.n;
+    b.slot_off[k] = g.slot_offset;
+    b.block_first[k] = int32_t(blocks);
+    blocks += ceil_div(g.n, kSumBlockElems);
+    if (blocks >= (int64_t(1) << 30)) return GN_ERR_RANGE;
+  }
+  if (b.n_segs == 0) return GN_OK;
+  b.block_first[b.n_segs] = int32_t(blocks);
+  GN_LAUNCH(slot_sum_kernel, (unsigned)blocks, 256, 0, as_stream(stream), static_cast<const char*>(buf), world,
+            slot_bytes, b);
   return GN_OK;
 }

@@ -9,6 +9,7 @@
 namespace gn {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_last_cuda_error{0};
 
 int bits_for(int64_t n_values) {
   int b = 1;
@@ -231,7 +232,7 @@ __global__ void chunk_fill_kernel(const int32_t* __restrict__ rowptr, const int3
 }
 
 // small CSRs (decoder structures rebuilt every epoch): count + scan + fill in ONE block
-constexpr int kChunkOneBlockRows = 8192;
+constexpr int kChunkOneBlockRows = 32768;
 __global__ void __launch_bounds__(1024) chunk_one_block_kernel(const int32_t* __restrict__ rowptr, int32_t n_rows,
                                                                int32_t chunk_len, int32_t* __restrict__ chunk_ptr,
                                                                int32_t* __restrict__ chunk_row,
@@ -297,6 +298,12 @@ extern "C" {
 int gn_version(void) { return 100; }
 
 uint64_t gn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gn_last_cuda_error(void) { return g_last_cuda_error.load(std::memory_order_relaxed); }
+
+const char* gn_last_cuda_error_string(void) {
+  return cudaGetErrorString(cudaError_t(g_last_cuda_error.load(std::memory_order_relaxed)));
+}
 
 const char* gn_error_string(int status) {
   switch (status) {

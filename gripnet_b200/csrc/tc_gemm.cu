@@ -160,8 +160,28 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // ---------------------------------------------------------------------------------------
 // B image: hi/lo split of op(B), laid out exactly as one smem stage wants it
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) b_image_kernel(const float* __restrict__ B, int64_t ldb, int transB, int K, int N,
-                                                      int nt, int n_kb, char* __restrict__ image) {
+// op(B)[k, n] for the four layouts of B the callers have:
+//   0  B stored [K, N]:  B[k*ldb + n]                 1  B stored [N, K] (op = transpose):  B[n*ldb + k]
+//   2  relation-batched along N (forward of myRGCN, Y[:, r, :] = X W[r], W stored [R][K][inner]):
+//        n = r*inner + c  ->  B[r*stride + k*ldb + c]
+//   3  relation-batched along K (dX = sum_r dY[:, r, :] W[r]^T):
+//        k = r*inner + c  ->  B[r*stride + n*ldb + c]
+struct BView {
+  const float* B;
+  int64_t ldb, stride;
+  int mode, inner;
+  __device__ __forceinline__ float at(int k, int n) const {
+    switch (mode) {
+      case 0: return __ldg(B + int64_t(k) * ldb + n);
+      case 1: return __ldg(B + int64_t(n) * ldb + k);
+      case 2: return __ldg(B + int64_t(n / inner) * stride + int64_t(k) * ldb + (n % inner));
+      default: return __ldg(B + int64_t(k / inner) * stride + int64_t(n) * ldb + (k % inner));
+    }
+  }
+};
+
+__global__ void __launch_bounds__(256) b_image_kernel(const BView bv, int K, int N, int nt, int n_kb,
+                                                      char* __restrict__ image) {
   // one thread per (n_tile, k_block, chunk, row)
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int n_tiles = (N + nt - 1) / nt;
@@ -177,7 +197,7 @@ __global__ void __launch_bounds__(256) b_image_kernel(const float* __restrict__ 
   for (int e = 0; e < 4; ++e) {
     const int k = kb * BK + c * 4 + e;
     float x = 0.f;
-    if (n < N && k < K) x = transB ? __ldg(B + int64_t(n) * ldb + k) : __ldg(B + int64_t(k) * ldb + n);
+    if (n < N && k < K) x = bv.at(k, n);
     v[e] = x;
   }
   float4 hi, lo;
@@ -404,12 +424,12 @@ struct Plan {
   size_t image_bytes, smem_bytes;
 };
 
-static Plan make_plan(int M, int N, int K) {
+static Plan make_plan(int M, int N, int K, int nt_cap = kMaxNt) {
   Plan pl{};
   pl.ok = false;
   if (M <= 0 || N <= 0 || K <= 0) return pl;
   const int n16 = (N + 15) / 16 * 16;
-  pl.nt = n16 <= kMaxNt ? n16 : kMaxNt;
+  pl.nt = n16 <= nt_cap ? n16 : nt_cap;
   pl.n_tiles = (N + pl.nt - 1) / pl.nt;
   pl.n_kb = (K + BK - 1) / BK;
   pl.stages = pl.nt <= 64 ? 2 : (pl.nt <= 128 ? 3 : 2);
@@ -433,6 +453,21 @@ static Plan make_plan(int M, int N, int K) {
 }  // namespace gn
 
 using namespace gn;
+
+static int tc_set_smem_attr() {
+  static std::atomic<int> attr_set{0};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      g_last_cuda_error.store(int(e), std::memory_order_relaxed);
+      return GN_ERR_CUDA;
+    }
+    attr_set.store(1, std::memory_order_release);
+  }
+  return GN_OK;
+}
 
 // B small enough for the B-producer warp to split it inside the main kernel (one N tile, <= 16 float4 per lane
 // and k-block): no prep launch.  Larger B (the [in, R*out] relation transform of pose-2) keeps the image.
@@ -460,8 +495,9 @@ extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const flo
   cudaStream_t st = as_stream(stream);
   if (!direct) {
     const int64_t total = int64_t(pl.n_tiles) * pl.n_kb * tc::CHUNKS * pl.nt;
-    GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, B, ldb, transB ? 1 : 0, K, N, pl.nt,
-              pl.n_kb, static_cast<char*>(ws));
+    const tc::BView bv{B, ldb, 0, transB ? 1 : 0, 1};
+    GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, bv, K, N, pl.nt, pl.n_kb,
+              static_cast<char*>(ws));
   }
   tc::Params p;
   p.M = M; p.N = N; p.K = K;
@@ -471,14 +507,60 @@ extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const flo
   p.B = B; p.ldb = ldb; p.transB = transB ? 1 : 0;
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
   p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
-  static std::atomic<int> attr_set{0};
-  if (!attr_set.load(std::memory_order_acquire)) {
-    if (cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return GN_ERR_CUDA;
-    }
-    attr_set.store(1, std::memory_order_release);
-  }
+  GN_CHECK(tc_set_smem_attr());
+  dim3 grid((unsigned)ceil_div(M, tc::BM), (unsigned)pl.n_tiles);
+  GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
+  return GN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// relation-batched feature transform of myRGCN on the tensor cores (north_star item 3):
+//   Y[:, r, :] = X W[r]   for every relation r at once  ==  Y[M, R*f] = X[M, K] . W_flat[K, R*f]
+// (gripnet/layers.py:171-189 evaluates it per edge as matmul(x_j[s:e], w[et]); transform-then-gather
+// evaluates it once per NODE and relation).  W is stored [R][K][f]; the B image is built from that layout
+// directly (BView mode 2), so no transposed copy of W exists.  The N tile is picked so that the grid can
+// fill the GPU when M is only a few hundred rows (the task supervertex of the pose family has 645 nodes).
+// ---------------------------------------------------------------------------------------
+static int rel_nt_cap(int M, int N) {
+  const int64_t m_tiles = ceil_div(M, tc::BM);
+  int cap = tc::kMaxNt;
+  while (cap > 32 && m_tiles * ceil_div(N, cap) < 148) cap >>= 1;
+  return cap;
+}
+
+extern "C" size_t gn_tc_gemm_rel_workspace_bytes(int32_t M, int32_t n_rel, int32_t f, int32_t K) {
+  const int64_t N = int64_t(n_rel) * f;
+  if (N <= 0 || N >= (int64_t(1) << 31)) return 0;
+  const tc::Plan pl = tc::make_plan(M, int(N), K, rel_nt_cap(M, int(N)));
+  return pl.ok ? align_up(pl.image_bytes) : 0;
+}
+
+extern "C" int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
+                              const float* W, float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream) {
+  if (M < 0 || n_rel <= 0 || f <= 0 || K <= 0 || !X || !W || !Y) return GN_ERR_ARG;
+  if (M == 0) return GN_OK;
+  const int64_t N64 = int64_t(n_rel) * f;
+  if (N64 >= (int64_t(1) << 31)) return GN_ERR_RANGE;
+  const int N = int(N64);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (!al16(X) || ldx % 4 != 0 || K % 4 != 0 || !al16(Y) || ldy % 4 != 0) return GN_ERR_ARG;
+  const tc::Plan pl = tc::make_plan(M, N, K, rel_nt_cap(M, N));
+  if (!pl.ok) return GN_ERR_ARG;
+  if (!ws || ws_bytes < pl.image_bytes || !al16(ws)) return GN_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  const int64_t total = int64_t(pl.n_tiles) * pl.n_kb * tc::CHUNKS * pl.nt;
+  const tc::BView bv{W, int64_t(f), int64_t(K) * f, 2, f};
+  GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, bv, K, N, pl.nt, pl.n_kb,
+            static_cast<char*>(ws));
+  tc::Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.A = X; p.lda = ldx; p.C = Y; p.ldc = ldy;
+  p.addend = nullptr; p.ldd = 0; p.mask = nullptr; p.ldm = 0;
+  p.b_image = static_cast<const char*>(ws);
+  p.B = W; p.ldb = f; p.transB = 0;
+  p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+  p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
+  GN_CHECK(tc_set_smem_attr());
   dim3 grid((unsigned)ceil_div(M, tc::BM), (unsigned)pl.n_tiles);
   GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
   return GN_OK;

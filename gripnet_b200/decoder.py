@@ -29,8 +29,6 @@ class multiRelaInnerProductDecoder(Module):
     def score_pair(self, z, pos_edge_index, neg_edge_index, edge_type, sigmoid=True):
         """``(forward(z, pos, et), forward(z, neg, et))`` of one training step
         (``GripNet-pose.py:133-138``) as one autograd node whose two halves run concurrently."""
-        if self.dist_ctx is None and ops.dense_decoder_ok(z, self.weight):       # experimental, off by default
-            return ops.DistMultPairDense.apply(z, self.weight, pos_edge_index, neg_edge_index, edge_type, bool(sigmoid))
         return ops.DistMultPair.apply(z, replicated(self.weight, self.dist_ctx), pos_edge_index, neg_edge_index,
                                       edge_type, bool(sigmoid))
 

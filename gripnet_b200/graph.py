@@ -251,27 +251,149 @@ def slice_csr(csr, r0, r1, n_cols):
     return Csr(rowptr, col, val, n_local, n_cols, b - a)
 
 
-class DistGcnGraph:
-    """This rank's rows of a destination-partitioned GCN graph (``parallel.py``).
+def filter_edges(edge_index, edge_weight, by_src, lo, hi, chunk=1 << 26):
+    """Order-preserving selection of the edges whose source (``by_src``) or destination lies in
+    ``[lo, hi)`` (``gn_edge_filter``; long lists go chunk by chunk).  Two passes: count every chunk, ONE
+    host read of the counts, then scatter into exactly sized outputs.
+    Returns ``(edge_index_local int64 [2, n], edge_weight_local or None)``."""
+    lib = _lib.load()
+    dev = edge_index.device
+    ei = edge_index.contiguous()
+    E = int(ei.size(1))
+    w = None if edge_weight is None else edge_weight.to(torch.float32).contiguous()
+    spans = [(a, min(E, a + chunk)) for a in range(0, E, chunk)]
+    counts = torch.zeros(max(len(spans), 1), dtype=torch.int32, device=dev)
+    ws = _ws(lib.gn_edge_filter_workspace_bytes(min(E, chunk)), dev)
+    for i, (a, b) in enumerate(spans):
+        _lib.check(lib.gn_edge_filter(_ptr(ei[0, a:]), _ptr(ei[1, a:]), None, b - a, int(by_src), int(lo), int(hi),
+                                      None, None, None, None, 0, _ptr(counts[i:]), _ptr(ws), ws.numel(), _stream()),
+                   "gn_edge_filter")
+    host = [int(v) for v in counts.tolist()]                      # one host read at graph-build time
+    total = sum(host)
+    out = torch.empty((2, max(total, 1)), dtype=torch.int64, device=dev)
+    out_w = torch.empty(max(total, 1), dtype=torch.float32, device=dev) if w is not None else None
+    scratch = torch.zeros(1, dtype=torch.int32, device=dev)
+    off = 0
+    for (a, b), c in zip(spans, host):
+        if c:
+            _lib.check(lib.gn_edge_filter(_ptr(ei[0, a:]), _ptr(ei[1, a:]), _ptr(w[a:]) if w is not None else None,
+                                          b - a, int(by_src), int(lo), int(hi), _ptr(out[0, off:]), _ptr(out[1, off:]),
+                                          _ptr(out_w[off:]) if out_w is not None else None, None, 0, _ptr(scratch),
+                                          _ptr(ws), ws.numel(), _stream()), "gn_edge_filter")
+        off += c
+    return out[:, :total], (out_w[:total] if out_w is not None else None)
 
-    ``fwd``: local TARGET rows of the dst-sorted CSR, columns = global source ids (the gathered
-    operand has ``world * b_src`` rows); ``bwd``: local SOURCE rows of the transpose CSR, columns =
-    global target ids.  ``n_src`` / ``n_dst`` are the LOCAL row counts the layer stacks see."""
+
+def part_structure(shard, weight, key_row, row0, n_rows, with_loops, fill, want_deg):
+    """Rows ``[row0, row0 + n_rows)`` of the CSR keyed by row ``key_row`` of ``shard`` (int64 ``[2, e]``, every
+    key inside the block; ``gn_gcn_part_structure``) -> ``(rowptr, col, val, deg, dis, nnz)``; ``val`` still
+    holds the per-entry weights (``part_values`` turns them into the GCN coefficients)."""
+    lib = _lib.load()
+    dev = shard.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    e = int(shard.size(1))
+    cap = max(e + (n_rows if with_loops else 0), 1)
+    rowptr = torch.empty(max(n_rows, 1) + 1, **i32)
+    col, val = torch.empty(cap, **i32), torch.empty(cap, **f32)
+    deg = torch.empty(max(n_rows, 1), **f32) if want_deg else None
+    dis = torch.empty(max(n_rows, 1), **f32) if want_deg else None
+    counts = torch.zeros(4, **i32)
+    if n_rows <= 0:
+        rowptr.zero_()
+        return rowptr, col, val, deg, dis, 0
+    ws = _ws(lib.gn_gcn_part_workspace_bytes(e, n_rows), dev)
+    _lib.check(lib.gn_gcn_part_structure(
+        _ptr(shard[key_row]) if e else None, _ptr(shard[1 - key_row]) if e else None, _ptr(weight), e, int(row0),
+        int(n_rows), int(with_loops), float(fill), _ptr(rowptr), _ptr(col), _ptr(val), _ptr(deg), _ptr(dis),
+        _ptr(counts), _ptr(ws), ws.numel(), _stream()), "gn_gcn_part_structure")
+    return rowptr, col, val, deg, dis, _host_int(counts[0])
+
+
+def part_values(rowptr, col, val, n_rows, row0, dis_src, dis_dst, transpose):
+    """``val <- (dis_src[source] * w) * dis_dst[target]`` with GLOBAL ``deg^-1/2`` vectors (``gn_gcn_part_values``)."""
+    if n_rows > 0:
+        _lib.check(_lib.load().gn_gcn_part_values(_ptr(rowptr), _ptr(col), int(n_rows), int(row0), _ptr(dis_src),
+                                                  _ptr(dis_dst), int(bool(transpose)), _ptr(val), _stream()),
+                   "gn_gcn_part_values")
+
+
+class DistGcnGraph:
+    """This rank's rows of a destination-partitioned GCN graph (``parallel.py``), built from this rank's
+    edges ONLY: the edges whose destination lies in its block give the rows of the dst-sorted CSR
+    (``fwd``: local TARGET rows, columns = global source ids — the gathered operand has ``world * b_src``
+    rows), the edges whose source lies in its block give the rows of the transpose CSR (``bwd``: local
+    SOURCE rows, columns = global target ids).  No rank sorts or stores the global CSR; the only global
+    quantity is the ``deg^-1/2`` vector (one float per node), all-gathered once at build time.  Rows are
+    bit-identical to the matching rows of the single-GPU ``GcnGraph``.
+    ``n_src`` / ``n_dst`` are the LOCAL row counts the layer stacks see."""
 
     def __init__(self, edge_index, spec, edge_weight=None, improved=False, bipartite=False):
+        import torch.distributed as dist
         ctx = spec.ctx
-        g = GcnGraph(edge_index, spec.n_src, spec.n_dst, edge_weight, improved, bipartite)   # replicated prep
+        dev = edge_index.device
         self.ctx, self.bipartite = ctx, bool(bipartite)
-        self.n_src_global, self.n_dst_global, self.n_edges = spec.n_src, spec.n_dst, g.n_edges
+        self.n_src_global, self.n_dst_global = spec.n_src, spec.n_dst
         self.b_src, self.b_dst = ctx.block(spec.n_src), ctx.block(spec.n_dst)
         s0, s1 = ctx.bounds(spec.n_src)
         d0, d1 = ctx.bounds(spec.n_dst)
         self.src_bounds, self.dst_bounds = (s0, s1), (d0, d1)
         self.n_src, self.n_dst = s1 - s0, d1 - d0
-        self.fwd = slice_csr(g.fwd, d0, d1, ctx.world * self.b_src)
-        self.bwd = slice_csr(g.bwd, s0, s1, ctx.world * self.b_dst)
-        self.nnz = self.fwd.nnz
-        self.deg, self.indeg = g.deg[d0:d1].clone(), g.indeg[d0:d1].clone()
+        if spec.n_src >= 2 ** 31 or spec.n_dst >= 2 ** 31:
+            raise RuntimeError("gripnet_b200: node counts must be < 2^31")
+        if spec.shards is None:
+            require_cuda(edge_index, "edge_index", torch.int64)
+            if edge_index.dim() != 2 or edge_index.size(0) != 2:
+                raise RuntimeError("edge_index must have shape [2, E]")
+            self.n_edges = int(edge_index.size(1))
+            if self.n_edges > 0:
+                lo, hi0, hi1 = int(edge_index.min()), int(edge_index[0].max()), int(edge_index[1].max())
+                if lo < 0 or hi0 >= spec.n_src or hi1 >= spec.n_dst:
+                    raise IndexError("edge_index out of range for the given node counts")
+            by_dst, w_dst = filter_edges(edge_index, edge_weight, False, d0, d1)
+            by_src, w_src = filter_edges(edge_index, edge_weight, True, s0, s1)
+        else:                       # the caller streamed the generator / loader through filter_edges itself
+            (by_dst, w_dst), (by_src, w_src) = spec.shards
+            self.n_edges = int(spec.n_edges_global)
+        fill = 2.0 if improved else 1.0
+        with_loops = 0 if bipartite else 1
+        f32 = dict(dtype=torch.float32, device=dev)
+        rowptr, col, val, deg, dis, nnz = part_structure(by_dst.contiguous(), w_dst, 1, d0, self.n_dst, with_loops,
+                                                         fill, True)
+        # the one global quantity: deg^-1/2 of every target node (block-padded so index == global node id)
+        dis_all = torch.zeros(ctx.world * self.b_dst, **f32)
+        dis_all[ctx.rank * self.b_dst: ctx.rank * self.b_dst + self.n_dst].copy_(dis[: self.n_dst])
+        if ctx.world > 1:
+            streams.effective_stream().synchronize()
+            dist.all_gather_into_tensor(dis_all, dis_all[ctx.rank * self.b_dst:(ctx.rank + 1) * self.b_dst].clone(),
+                                        group=ctx.group)
+        dis_src = None if bipartite else dis_all
+        part_values(rowptr, col, val, self.n_dst, d0, dis_src, dis_all, False)
+        self.fwd = Csr(rowptr, col, val, self.n_dst, ctx.world * self.b_src, nnz)
+        rowptr_t, col_t, val_t, _, _, nnz_t = part_structure(by_src.contiguous(), w_src, 0, s0, self.n_src,
+                                                             with_loops, fill, False)
+        part_values(rowptr_t, col_t, val_t, self.n_src, s0, dis_src, dis_all, True)
+        self.bwd = Csr(rowptr_t, col_t, val_t, self.n_src, ctx.world * self.b_dst, nnz_t)
+        self.nnz = nnz
+        self.deg = deg[: self.n_dst]
+        self.indeg = (rowptr[1: self.n_dst + 1] - rowptr[: self.n_dst]).to(torch.int32)
+        # share of the operand rows this rank's forward rows actually reference (halo statistics): with the
+        # uniformly random / hashed R-MAT graphs of the benchmarks it is ~1, which is why the exchange is a full
+        # slot all-gather rather than a packed halo
+        self._halo = None
+
+    def halo_fraction(self):
+        """Fraction of the REMOTE operand rows referenced by this rank's forward rows (one pass, cached)."""
+        if self._halo is None:
+            n_cols = self.ctx.world * self.b_src
+            seen = torch.zeros(n_cols, dtype=torch.bool, device=self.fwd.col.device)
+            if self.fwd.nnz > 0:
+                seen[self.fwd.col[: self.fwd.nnz].long()] = True
+            s0, s1 = self.src_bounds
+            remote = int(seen.sum()) - int(seen[s0:s1].sum())
+            total_remote = max(self.n_src_global - (s1 - s0), 1)
+            self._halo = remote / total_remote
+        return self._halo
 
 
 class DistRgcnGraph:
@@ -319,6 +441,32 @@ class EdgeStruct:
                                     _ptr(self.ent_eid), None, None, _ptr(ws), ws.numel(),
                                     _stream()), "gn_edge_prep")
         self.node = Csr(node_rowptr, self.ent_other, None, n_nodes, n_nodes, 2 * E, exact=exact)
+
+
+class PairStruct:
+    """(node, relation) pair CSR of an edge list — rows = ``node * n_rel + rel``, entries = (other endpoint,
+    edge id) — for the one-gather-pass DistMult backward (``gn_pair_prep`` / ``gn_distmult_bwd_pairs``)."""
+
+    def __init__(self, edge_index, edge_type, n_nodes, n_rel, exact):
+        lib = _lib.load()
+        dev = edge_index.device
+        E = int(edge_index.size(1))
+        if 2 * E >= 2 ** 31 or n_nodes * n_rel >= 2 ** 31:
+            raise RuntimeError("gripnet_b200: 2*E and num_nodes * num_relations must be < 2^31")
+        ei = edge_index.contiguous()
+        et = edge_type.contiguous()
+        self.edge_index, self.edge_type = ei, et
+        self.n_nodes, self.n_rel = int(n_nodes), int(n_rel)
+        i32 = dict(dtype=torch.int32, device=dev)
+        n_rows = n_nodes * n_rel
+        rowptr = torch.empty(n_rows + 1, **i32)
+        self.ent_other = torch.empty(max(2 * E, 1), **i32)
+        self.ent_eid = torch.empty(max(2 * E, 1), **i32)
+        ws = _ws(lib.gn_pair_prep_workspace_bytes(E), dev)
+        _lib.check(lib.gn_pair_prep(_ptr(ei[0]) if E else None, _ptr(ei[1]) if E else None, _ptr(et) if E else None,
+                                    E, n_nodes, n_rel, _ptr(rowptr), _ptr(self.ent_other), _ptr(self.ent_eid),
+                                    _ptr(ws), ws.numel(), _stream()), "gn_pair_prep")
+        self.csr = Csr(rowptr, self.ent_other, None, n_rows, n_nodes, 2 * E, exact=exact)
 
 
 class IndexStruct:
@@ -385,6 +533,47 @@ def _capturing():
     return torch.cuda.is_current_stream_capturing()
 
 
+# --------------------------------------------------------------------------
+# index validation for the decoder paths (the kernels address  z + src[e]*ldz,  w + etype[e]*D,
+# score[i*C + label[i]]  directly: an out-of-range id would be a silent out-of-bounds device read where
+# the reference raises IndexError).  One host check (min / max) per (tensor identity, version, bound),
+# remembered in an LRU; skipped while a CUDA graph is being captured (the eager warm-up iterations that
+# precede every capture have validated the same buffers).
+# --------------------------------------------------------------------------
+_validated = OrderedDict()
+_VALIDATED_CAPACITY = 256
+
+
+def mark_valid(t, hi):
+    """Record that every entry of ``t`` lies in ``[0, hi)`` (producers that guarantee it by construction,
+    e.g. the device negative sampler, call this instead of paying the host check)."""
+    key = (_Cache.tkey(t), int(hi))
+    _validated[key] = True
+    _validated.move_to_end(key)
+    while len(_validated) > _VALIDATED_CAPACITY:
+        _validated.popitem(last=False)
+
+
+def validate_index(t, hi, name):
+    """Raise IndexError unless every entry of the int64 CUDA tensor ``t`` lies in ``[0, hi)``."""
+    if t is None or t.numel() == 0:
+        return
+    key = (_Cache.tkey(t), int(hi))
+    if key in _validated:
+        _validated.move_to_end(key)
+        return
+    if _capturing():
+        return
+    s = streams.override()
+    if s is not None:
+        s.synchronize()
+    lo, mx = torch.aminmax(t)
+    lo, mx = int(lo.item()), int(mx.item())
+    if lo < 0 or mx >= hi:
+        raise IndexError(f"gripnet_b200: {name} holds ids in [{lo}, {mx}] but the valid range is [0, {int(hi)})")
+    mark_valid(t, hi)
+
+
 def gcn_graph(edge_index, n_src, n_dst, edge_weight=None, improved=False, bipartite=False, want_aug=False):
     from . import parallel
     spec = parallel.lookup(edge_index)
@@ -397,14 +586,22 @@ def gcn_graph(edge_index, n_src, n_dst, edge_weight=None, improved=False, bipart
                       lambda: GcnGraph(edge_index, n_src, n_dst, edge_weight, improved, bipartite, want_aug))
 
 
+def _range_key(range_list):
+    """Cache key of a ``range_list`` given as a tensor, ndarray or nested list (the reference passes an
+    ndarray-backed tensor, utils.py:141-148): tensors by identity + version, anything else by value."""
+    if torch.is_tensor(range_list):
+        return _Cache.tkey(range_list)
+    return tuple(int(v) for v in torch.as_tensor(range_list).flatten().tolist())
+
+
 def rgcn_graph(edge_index, range_list, n_nodes, n_rel):
     from . import parallel
     spec = parallel.lookup(edge_index)
     if spec is not None:
-        key = ("drgcn", _Cache.tkey(edge_index), _Cache.tkey(range_list), n_rel, spec.ctx.rank)
+        key = ("drgcn", _Cache.tkey(edge_index), _range_key(range_list), n_rel, spec.ctx.rank)
         return _cache.get(key, (edge_index, range_list),
                           lambda: DistRgcnGraph(edge_index, range_list, spec, n_rel))
-    key = ("rgcn", _Cache.tkey(edge_index), _Cache.tkey(range_list), n_nodes, n_rel)
+    key = ("rgcn", _Cache.tkey(edge_index), _range_key(range_list), n_nodes, n_rel)
     return _cache.get(key, (edge_index, range_list), lambda: RgcnGraph(edge_index, range_list, n_nodes, n_rel))
 
 
@@ -413,6 +610,13 @@ def edge_struct(edge_index, edge_type, n_nodes, n_rel):
     exact = not _capturing()
     return _cache.get(key, (edge_index, edge_type),
                       lambda: EdgeStruct(edge_index, edge_type, n_nodes, n_rel, exact))
+
+
+def pair_struct(edge_index, edge_type, n_nodes, n_rel):
+    key = ("pair", _Cache.tkey(edge_index), _Cache.tkey(edge_type), n_nodes, n_rel)
+    exact = not _capturing()
+    return _cache.get(key, (edge_index, edge_type),
+                      lambda: PairStruct(edge_index, edge_type, n_nodes, n_rel, exact))
 
 
 def rel_struct(edge_type, n_rel):

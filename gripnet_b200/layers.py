@@ -193,14 +193,10 @@ class homoGraph(Module):
                 c._graph_source = convs[0]._graph_source
             params = [p for c in convs for p in (c.weight, c.bias)]
             return ops.GcnStack.apply(x, g, relu, bool(if_catout), *params)
-        # foreign layer types in conv_list: layer-by-layer
-        outs = [x]
-        for net in convs:
-            x = net(x, homo_edge_index, edge_type, range_list) if self.multi_relational \
-                else net(x, homo_edge_index, edge_weight)
-            x = torch.relu(x)
-            outs.append(x)
-        return torch.cat(outs, dim=1) if if_catout else x
+        # conv_list is an ordinary ModuleList, so a caller could swap a layer for a foreign module; this package
+        # has no eager PyTorch path to run it with
+        raise RuntimeError("gripnet_b200.homoGraph: conv_list must hold only this package's myGCN (or, when "
+                           "multi_relational, myRGCN) layers")
 
 
 class interGraph(Module):

@@ -14,7 +14,7 @@ import os
 import torch
 
 from . import _lib, streams
-from .graph import _ptr, _stream, _ws, require_cuda
+from .graph import _ptr, _stream, _ws, require_cuda, validate_index
 
 EPS = 1e-13  # reference gripnet/utils.py:10
 
@@ -140,6 +140,24 @@ def sgemm(ta, tb, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, device, batch=1, 
                             _ptr(a_rows), 1 if ws is not None else 0, _ptr(ws), ws_bytes, _stream()), "gn_sgemm")
 
 
+# relation transform Y[:, r, :] = X W[r]: tensor cores whenever the 3xTF32 kernel's alignment rules hold
+# ("ffma" keeps it on the CUDA cores — the A/B switch of the config-4 measurements)
+def rel_transform(x, w, y, r, k, f, device):
+    """``x``: M view [n, k]; ``w``: contiguous [r, k, f] tensor; ``y``: M view [n, r*f]."""
+    lib = _lib.load()
+    n = x.n
+    if n == 0:
+        return
+    if GEMM_PATH != "ffma" and k % 4 == 0 and x.ld % 4 == 0 and y.ld % 4 == 0 and x.ptr % 16 == 0 and y.ptr % 16 == 0:
+        nbytes = int(lib.gn_tc_gemm_rel_workspace_bytes(n, r, f, k))
+        if nbytes:
+            img = _ws(nbytes, device)
+            _lib.check(lib.gn_tc_gemm_rel(n, r, f, k, x.ptr, x.ld, w.data_ptr(), y.ptr, y.ld, _ptr(img), nbytes,
+                                          _stream()), "gn_tc_gemm_rel")
+            return
+    sgemm(False, False, n, f, k, x.ptr, x.ld, w.data_ptr(), f, y.ptr, y.ld, device, batch=r, sa=0, sb=k * f, sc=f)
+
+
 def map2d(op, src, dst):
     _lib.check(_lib.load().gn_map2d(op, src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.f, _stream()), "gn_map2d")
 
@@ -179,7 +197,7 @@ class GcnStack(torch.autograd.Function):
         dctx = getattr(graph, "ctx", None)
         b_src = graph.b_src if dctx is not None else None
         outs = []      # M views of H_0 .. H_L
-        br = streams.Branch(enabled=dctx is None)
+        br = streams.Branch()                  # no collective is ever issued inside a branch
         if catout:
             buf = _new(graph.n_dst, sum(dims), x0)
             offs = [sum(dims[:i]) for i in range(len(dims))]
@@ -310,7 +328,7 @@ class RgcnStack(torch.autograd.Function):
         dctx = getattr(graph, "ctx", None)
         blk = graph.b if dctx is not None else None
         outs, ws_list = [], []
-        br = streams.Branch(enabled=dctx is None)
+        br = streams.Branch()                  # no collective is ever issued inside a branch
         if catout:
             buf = _new(n, sum(dims), x0)
             offs = [sum(dims[:i]) for i in range(len(dims))]
@@ -336,12 +354,18 @@ class RgcnStack(torch.autograd.Function):
             # accumulates onto it
             with br(xin.t, rt, hl.t):
                 sgemm(False, False, n, f, k, xin.ptr, xin.ld, rt.data_ptr(), f, hl.ptr, hl.ld, dev)
-            # Y[:, r, :] = X W[r] for every relation at once (transform-then-gather)
-            y = Slot(n, r * f, x0, dctx, blk)
-            sgemm(False, False, n, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, r * f, dev,
-                  batch=r, sa=0, sb=k * f, sc=f)
+            # Y[:, r, :] = X W[r] for every relation at once (transform-then-gather), on the tensor cores.
+            # Partitioned run: the NARROW layer input (k floats per node) is what crosses NVLink, and every
+            # rank transforms all the gathered rows itself — R*f/k times fewer bytes exchanged than gathering Y
+            if dctx is not None:
+                xs = Slot(n, k, x0, dctx, blk)
+                map2d(_lib.EW_COPY, xin, xs.m)
+                xall = xs.gather()
+            else:
+                xall = xin
+            yfull = _new(xall.n, r * f, x0)
+            rel_transform(xall, w, M(yfull), r, k, f, dev)
             b = bias[l].contiguous() if bias[l] is not None else None
-            yfull = y.gather().t
             br.join()
             spmm(graph.fwd, M(yfull.view(yfull.size(0) * r, f)), hl, f, row_scale=graph.inv_cnt, bias=b, addend=hl,
                  relu=relu_flags[l])
@@ -462,6 +486,32 @@ def axpby(a, alpha, b, beta, dst):
                                     _stream()), "gn_axpby")
 
 
+class Mean3(torch.autograd.Function):
+    """``(a + b + c) / 3`` (``GripNet-freebase-d.py:160-161``) as one kernel; backward ``g / 3`` once, shared."""
+
+    @staticmethod
+    def forward(ctx, a, b, c):
+        a, b, c = _as_rows(a, "a"), _as_rows(b, "b"), _as_rows(c, "c")
+        if a.shape != b.shape or a.shape != c.shape:
+            raise RuntimeError("mean3: the three inputs must have the same shape")
+        out = _new(a.size(0), a.size(1), a)
+        ma, mb, mc, mo = M(a), M(b), M(c), M(out)
+        _lib.check(_lib.load().gn_mean3(ma.ptr, ma.ld, mb.ptr, mb.ld, mc.ptr, mc.ld, mo.ptr, mo.ld, ma.n, ma.f,
+                                        _stream()), "gn_mean3")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _as_rows(g, "grad")
+        dg = _new(g.size(0), g.size(1), g)
+        axpby(M(g), 1.0 / 3.0, None, 0.0, M(dg))
+        return dg, dg, dg
+
+
+def mean3(a, b, c):
+    return Mean3.apply(a, b, c)
+
+
 def abs_bwd(g, t, dst, scale):
     _lib.check(_lib.load().gn_abs_bwd(g.ptr, g.ld, t.ptr, t.ld, dst.ptr, dst.ld, g.n, g.f, float(scale),
                                       _stream()), "gn_abs_bwd")
@@ -539,39 +589,20 @@ def _distmult_check(z, weight, edge_index, edge_type):
         raise RuntimeError("edge_index must be [2,E] and edge_type [E]")
     if w.size(1) != z.size(1):
         raise RuntimeError("decoder weight width must equal the embedding width")
+    validate_index(edge_index, z.size(0), "edge_index")          # the reference raises IndexError here too
+    validate_index(edge_type, w.size(0), "edge_type")
     return z, w, edge_index.contiguous(), edge_type.contiguous()
 
 
-# decoder path: "global" = the global-memory gather kernels (decoder.cu); "auto" keeps the embedding table in
-# shared memory whenever it fits one SM (decoder_resident.cu; the task supervertex of every pose dataset is
-# 645 x 80 floats), "resident" insists on it.  Measured on B200 (profiles/r01_v7_*): the resident family is
-# NOT faster — the decoder is bound by the latency of its index / coefficient streams at the occupancy one
-# 206 KB CTA per SM allows, not by the L1 row gathers — so the default stays "global".
-DECODER_PATH = os.environ.get("GRIPNET_B200_DECODER", "global")
-DW_IDENTITY = os.environ.get("GRIPNET_B200_DW_IDENTITY", "1") != "0"
-
-
-def _z_resident(z):
-    if DECODER_PATH == "global":
-        return False
-    n, d = z.size(0), z.size(1)
-    ok = bool(_lib.load().gn_distmult_resident_ok(n, d, z.stride(0) if n > 1 else d)) and z.data_ptr() % 16 == 0
-    if DECODER_PATH == "resident" and not ok:
-        raise RuntimeError("GRIPNET_B200_DECODER=resident: the embedding table does not fit shared memory")
-    return ok
+def _ldz(z):
+    return z.stride(0) if z.size(0) > 1 else z.size(1)
 
 
 def _distmult_fwd(z, w, ei, et, sigmoid):
     e = ei.size(1)
     out = torch.empty(e, dtype=torch.float32, device=z.device)
-    if e and _z_resident(z) and w.data_ptr() % 16 == 0:
-        _lib.check(_lib.load().gn_distmult_fwd_resident(z.data_ptr(), z.stride(0) if z.size(0) > 1 else z.size(1),
-                                                        z.size(0), z.size(1), w.data_ptr(), _ptr(ei[0]), _ptr(ei[1]),
-                                                        _ptr(et), e, int(sigmoid), _ptr(out), _stream()),
-                   "gn_distmult_fwd_resident")
-        return out
-    _lib.check(_lib.load().gn_distmult_fwd(z.data_ptr(), z.stride(0) if z.size(0) > 1 else z.size(1), z.size(1),
-                                           w.data_ptr(), _ptr(ei[0]) if e else None, _ptr(ei[1]) if e else None,
+    _lib.check(_lib.load().gn_distmult_fwd(z.data_ptr(), _ldz(z), z.size(1), w.data_ptr(),
+                                           _ptr(ei[0]) if e else None, _ptr(ei[1]) if e else None,
                                            _ptr(et) if e else None, e, int(sigmoid), _ptr(out), _stream()),
                "gn_distmult_fwd")
     return out
@@ -585,67 +616,63 @@ def _distmult_coef(g, out, sigmoid):
     return coef
 
 
-def _distmult_dz(key_tensors, coef, z, w):
-    """dz[i] = sum over the endpoint-CSR row of node i of coef_e * z[other] * w[rel]  (atomic-free)."""
-    from .graph import edge_struct
+def _pair_walk(ps, coef, z):
+    """T[n, r, :] = sum over the pair row (n, r) of coef[e] * z[other]  (one gather pass, atomic-free)."""
+    d = z.size(1)
+    t = torch.empty((ps.csr.n_rows, d), dtype=torch.float32, device=z.device)
+    part = ps.csr.partial(d)
+    _lib.check(_lib.load().gn_distmult_bwd_pairs(ps.csr.ref, _ptr(ps.ent_other), _ptr(ps.ent_eid), _ptr(coef),
+                                                 z.data_ptr(), _ldz(z), d, t.data_ptr(), _ptr(part), _stream()),
+               "gn_distmult_bwd_pairs")
+    return t
+
+
+def _distmult_grads(t, t2, z, w, need_z, need_w):
     n, d, r = z.size(0), z.size(1), w.size(0)
-    es = edge_struct(key_tensors[0], key_tensors[1], n, r)
-    dz = torch.empty((n, d), dtype=torch.float32, device=z.device)
-    part = es.node.partial(d)
-    if _z_resident(z) and w.data_ptr() % 16 == 0:
-        _lib.check(_lib.load().gn_distmult_bwd_z_resident(
-            es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid), _ptr(coef), z.data_ptr(),
-            z.stride(0) if n > 1 else d, d, w.data_ptr(), dz.data_ptr(), d, _ptr(part), _stream()),
-            "gn_distmult_bwd_z_resident")
-        return dz
-    _lib.check(_lib.load().gn_distmult_bwd_z(es.node.ref, _ptr(es.ent_other), _ptr(es.ent_rel), _ptr(es.ent_eid),
-                                             _ptr(coef), z.data_ptr(), z.stride(0) if n > 1 else d, d, w.data_ptr(),
-                                             dz.data_ptr(), d, _ptr(part), _stream()), "gn_distmult_bwd_z")
-    return dz
+    dz = torch.empty((n, d), dtype=torch.float32, device=z.device) if need_z else None
+    dw = torch.empty_like(w) if need_w else None
+    if need_z or need_w:
+        _lib.check(_lib.load().gn_distmult_grads(t.data_ptr(), _ptr(t2), n, r, d, z.data_ptr(), _ldz(z), w.data_ptr(),
+                                                 _ptr(dz), d, _ptr(dw), _stream()), "gn_distmult_grads")
+    return dz, dw
 
 
-def _distmult_dw(dw, edge_type_key, ei, coef, z, alt=False):
-    """dw[r] = sum over the relation-CSR row r of coef_e * z[src_e] * z[dst_e], into the caller's ``dw``.
-    ``alt``: use the CSR's second set of arrival counters (a concurrent walk of the same CSR)."""
-    from .graph import rel_struct
-    n, d, r, e = z.size(0), z.size(1), dw.size(0), ei.size(1)
-    rs = rel_struct(edge_type_key, r)
-    part = rs.csr.partial(d)
-    perm = None if (rs.identity and DW_IDENTITY) else _ptr(rs.perm)     # relation-major list: entry s is edge s
-    if e and _z_resident(z):
-        _lib.check(_lib.load().gn_distmult_bwd_w_resident(
-            rs.csr.alt_ref() if alt else rs.csr.ref, perm, _ptr(ei[0]), _ptr(ei[1]), _ptr(coef), z.data_ptr(),
-            z.stride(0) if n > 1 else d, n, d, dw.data_ptr(), _ptr(part), _stream()), "gn_distmult_bwd_w_resident")
-        return
-    _lib.check(_lib.load().gn_distmult_bwd_w(rs.csr.alt_ref() if alt else rs.csr.ref, perm, _ptr(ei[0]) if e else None,
-                                             _ptr(ei[1]) if e else None, _ptr(coef), z.data_ptr(),
-                                             z.stride(0) if n > 1 else d, d, dw.data_ptr(), _ptr(part), _stream()),
-               "gn_distmult_bwd_w")
+def _check_versions(tensors, versions, what):
+    """The backward's index structures are keyed on the LIVE index tensors: an in-place rewrite between
+    forward and backward (e.g. ``sampler.sample(out=buf)``) would silently pair the saved scores with
+    another edge list."""
+    for t, v in zip(tensors, versions):
+        if t._version != v:
+            raise RuntimeError(f"gripnet_b200: {what} was modified in place between forward and backward")
 
 
 class DistMult(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, weight, edge_index, edge_type, sigmoid):
+        from .graph import pair_struct
         z, w, ei, et = _distmult_check(z, weight, edge_index, edge_type)
+        need = torch.is_grad_enabled() and (z.requires_grad or weight.requires_grad)
+        br = streams.Branch()
+        if need:      # the (node, relation) structure depends on the indices only: built next to the scores
+            with br(edge_index, edge_type):
+                pair_struct(edge_index, edge_type, z.size(0), w.size(0))
         out = _distmult_fwd(z, w, ei, et, sigmoid)
+        br.join()
         ctx.sigmoid = bool(sigmoid)
         ctx.key_tensors = (edge_index, edge_type)
-        ctx.save_for_backward(z, w, out, ei, et)
+        ctx.key_versions = (edge_index._version, edge_type._version)
+        ctx.save_for_backward(z, w, out)
         return out
 
     @staticmethod
     def backward(ctx, grad):
-        z, w, out, ei, et = ctx.saved_tensors
+        from .graph import pair_struct
+        z, w, out = ctx.saved_tensors
+        _check_versions(ctx.key_tensors, ctx.key_versions, "edge_index / edge_type")
         coef = _distmult_coef(grad.contiguous(), out, ctx.sigmoid)
-        dz = dw = None
-        br = streams.Branch()
-        if ctx.needs_input_grad[1]:                      # dw next to dz: they only share `coef`
-            dw = torch.empty_like(w)
-            with br(coef, z, ei):
-                _distmult_dw(dw, ctx.key_tensors[1], ei, coef, z)
-        if ctx.needs_input_grad[0]:
-            dz = _distmult_dz(ctx.key_tensors, coef, z, w)
-        br.join()
+        ps = pair_struct(ctx.key_tensors[0], ctx.key_tensors[1], z.size(0), w.size(0))
+        t = _pair_walk(ps, coef, z)
+        dz, dw = _distmult_grads(t, None, z, w, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dz, dw, None, None, None
 
 
@@ -653,121 +680,54 @@ class DistMultPair(torch.autograd.Function):
     """Positive and negative edge lists of one training step scored together
     (``GripNet-pose.py:133-138`` calls the decoder twice on the same ``z`` and ``edge_type``).
 
-    Same kernels as two ``DistMult`` calls; the two lists are independent, so forward runs them on two
-    streams and backward on four (dz_pos | dz_neg | dw_pos | dw_neg; the two dw walk the shared relation
-    CSR with separate arrival counters), then ``dz = dz_pos + dz_neg`` and ``dw = dw_pos + dw_neg`` in
-    that fixed order — the same sums autograd forms for two separate calls.
+    Forward: the two lists are independent, so they run on two streams, next to the build of their
+    (node, relation) structures (the negatives' one is rebuilt on the device every step).  Backward: ONE
+    gather pass per list (``gn_distmult_bwd_pairs``, concurrently) and one kernel that forms
+    ``dz = sum_r (T_pos + T_neg)[n,r] .* w[r]`` and ``dw = 1/2 sum_n z[n] .* (T_pos + T_neg)[n,r]``.
     """
 
     @staticmethod
     def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid):
+        from .graph import pair_struct
         z, w, pi, et = _distmult_check(z, weight, pos_index, edge_type)
         _, _, ni, _ = _distmult_check(z, weight, neg_index, edge_type)
-        br = streams.Branch()
+        need = torch.is_grad_enabled() and (z.requires_grad or weight.requires_grad)
+        br, br_s = streams.Branch(), streams.Branch()
+        if need:
+            with br_s(pos_index, neg_index, edge_type):
+                pair_struct(neg_index, edge_type, z.size(0), w.size(0))
+                pair_struct(pos_index, edge_type, z.size(0), w.size(0))      # cached after the first step
         with br(z, w, ni, et):
             neg = _distmult_fwd(z, w, ni, et, sigmoid)
         pos = _distmult_fwd(z, w, pi, et, sigmoid)
         br.join()
+        br_s.join()
         ctx.sigmoid = bool(sigmoid)
         ctx.keys = (pos_index, neg_index, edge_type)
-        ctx.save_for_backward(z, w, pos, neg, pi, ni, et)
+        ctx.key_versions = tuple(t._version for t in ctx.keys)
+        ctx.save_for_backward(z, w, pos, neg)
         return pos, neg
 
     @staticmethod
     def backward(ctx, g_pos, g_neg):
-        z, w, pos, neg, pi, ni, et = ctx.saved_tensors
-        pos_key, neg_key, et_key = ctx.keys
-        need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        b_neg, b_wp = streams.Branch(), streams.Branch()
-        g_pos, g_neg = g_pos.contiguous(), g_neg.contiguous()
-        coef_p = _distmult_coef(g_pos, pos, ctx.sigmoid)
-        dz = dz_n = dw = dw_n = None
-        if need_w:
-            dw, dw_n = torch.empty_like(w), torch.empty_like(w)
-            with b_wp(coef_p, z, pi):
-                _distmult_dw(dw, et_key, pi, coef_p, z)
-        with b_neg(g_neg, neg, z, w):
-            coef_n = _distmult_coef(g_neg, neg, ctx.sigmoid)
-            b_wn = streams.Branch()                     # forks off b_neg's stream, behind coef_n
-            if need_w:
-                with b_wn(coef_n, z, ni):
-                    _distmult_dw(dw_n, et_key, ni, coef_n, z, alt=True)
-            if need_z:
-                dz_n = _distmult_dz((neg_key, et_key), coef_n, z, w)
-        if need_z:
-            dz = _distmult_dz((pos_key, et_key), coef_p, z, w)
-        b_wn.join()
-        b_neg.join()
-        if need_z:
-            axpby(M(dz), 1.0, M(dz_n), 1.0, M(dz))
-        b_wp.join()
-        if need_w:
-            axpby(M(dw), 1.0, M(dw_n), 1.0, M(dw))
-        return dz, dw, None, None, None, None
-
-
-# ----------------------------------------------------------------------------
-# dense-relation decoder — EXPERIMENTAL (parity-checked on a B200, not yet timed; GRIPNET_B200_DECODER=dense)
-# ----------------------------------------------------------------------------
-_DENSE_MAX_BYTES = 512 << 20          # S and C are [R, n, n] fp32 each
-
-
-def dense_decoder_ok(z, w):
-    return DECODER_PATH == "dense" and w.size(0) * z.size(0) * z.size(0) * 4 <= _DENSE_MAX_BYTES
-
-
-class DistMultPairDense(torch.autograd.Function):
-    """``DistMultPair`` for a small task supervertex with dense relation slices (csrc/decoder_dense.cu):
-    ``S_r = (z .* w_r) z^T`` once for both edge lists, scores by a 4-byte gather; backward through the summed
-    coefficient matrices ``C_r`` of BOTH lists and one batched product ``T_r = C_r z``."""
-
-    @staticmethod
-    def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid):
-        lib = _lib.load()
-        z, w, pi, et = _distmult_check(z, weight, pos_index, edge_type)
-        _, _, ni, _ = _distmult_check(z, weight, neg_index, edge_type)
-        n, d, r, e = z.size(0), z.size(1), w.size(0), pi.size(1)
-        dev, ldz = z.device, (z.stride(0) if z.size(0) > 1 else z.size(1))
-        zw = torch.empty((r, n, d), dtype=torch.float32, device=dev)
-        _lib.check(lib.gn_distmult_dense_scale(z.data_ptr(), ldz, n, d, w.data_ptr(), r, zw.data_ptr(), _stream()),
-                   "gn_distmult_dense_scale")
-        s = torch.empty((r, n, n), dtype=torch.float32, device=dev)
-        sgemm(False, True, n, n, d, zw.data_ptr(), d, z.data_ptr(), ldz, s.data_ptr(), n, dev, batch=r, sa=n * d, sb=0,
-              sc=n * n)
-        outs = []
-        for idx in (pi, ni):
-            out = torch.empty(e, dtype=torch.float32, device=dev)
-            _lib.check(lib.gn_distmult_dense_scores(s.data_ptr(), n, _ptr(idx[0]) if e else None,
-                                                    _ptr(idx[1]) if e else None, _ptr(et) if e else None, e,
-                                                    int(sigmoid), _ptr(out), _stream()), "gn_distmult_dense_scores")
-            outs.append(out)
-        ctx.sigmoid = bool(sigmoid)
-        ctx.keys = (pos_index, neg_index, edge_type)
-        ctx.save_for_backward(z, w, outs[0], outs[1])
-        return outs[0], outs[1]
-
-    @staticmethod
-    def backward(ctx, g_pos, g_neg):
-        from .graph import edge_struct
-        lib = _lib.load()
+        from .graph import pair_struct
         z, w, pos, neg = ctx.saved_tensors
         pos_key, neg_key, et_key = ctx.keys
-        n, d, r = z.size(0), z.size(1), w.size(0)
-        dev, ldz = z.device, (z.stride(0) if z.size(0) > 1 else z.size(1))
-        c = torch.empty((r, n, n), dtype=torch.float32, device=dev)
-        for first, (key, g, out) in enumerate(((pos_key, g_pos, pos), (neg_key, g_neg, neg))):
-            coef = _distmult_coef(g.contiguous(), out, ctx.sigmoid)
-            es = edge_struct(key, et_key, n, r)
-            _lib.check(lib.gn_distmult_dense_coef(_ptr(es.node.rowptr), _ptr(es.ent_other), _ptr(es.ent_rel),
-                                                  _ptr(es.ent_eid), _ptr(coef), n, r, int(first == 0), c.data_ptr(),
-                                                  _stream()), "gn_distmult_dense_coef")
-        t = torch.empty((r, n, d), dtype=torch.float32, device=dev)
-        sgemm(False, False, n, d, n, c.data_ptr(), n, z.data_ptr(), ldz, t.data_ptr(), d, dev, batch=r, sa=n * n, sb=0,
-              sc=n * d)
-        dz = torch.empty((n, d), dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
-        _lib.check(lib.gn_distmult_dense_grads(t.data_ptr(), n, d, r, z.data_ptr(), ldz, w.data_ptr(), _ptr(dz), d,
-                                               _ptr(dw), _stream()), "gn_distmult_dense_grads")
+        _check_versions(ctx.keys, ctx.key_versions, "pos / neg edge_index or edge_type")
+        n, r = z.size(0), w.size(0)
+        ps_p = pair_struct(pos_key, et_key, n, r)
+        ps_n = pair_struct(neg_key, et_key, n, r)
+        g_pos, g_neg = g_pos.contiguous(), g_neg.contiguous()
+        # one structure serves both lists when they are the same tensor: its arrival counters cannot be
+        # shared by two concurrent walks, so that case runs on one stream
+        br = streams.Branch(enabled=ps_p is not ps_n)
+        with br(g_neg, neg, z):
+            coef_n = _distmult_coef(g_neg, neg, ctx.sigmoid)
+            t_n = _pair_walk(ps_n, coef_n, z)
+        coef_p = _distmult_coef(g_pos, pos, ctx.sigmoid)
+        t_p = _pair_walk(ps_p, coef_p, z)
+        br.join()
+        dz, dw = _distmult_grads(t_p, t_n, z, w, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dz, dw, None, None, None, None
 
 
@@ -783,6 +743,7 @@ class MultiClass(torch.autograd.Function):
         require_cuda(node_list, "node_list", torch.int64)
         if w.size(0) != z.size(1):
             raise RuntimeError("decoder weight rows must equal the embedding width")
+        validate_index(node_list, z.size(0), "node_list")
         idx = node_list.contiguous().view(-1)
         m, d, c = idx.numel(), z.size(1), w.size(1)
         dev = z.device
@@ -863,6 +824,7 @@ class NodeClassLoss(torch.autograd.Function):
         labels = require_cuda(labels, "labels", torch.int64).contiguous()
         if labels.numel() != score.size(0):
             raise RuntimeError("labels must have one entry per score row")
+        validate_index(labels, score.size(1), "labels")
         dev = score.device
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         ws = _ws(lib.gn_loss_workspace_bytes(score.size(0)), dev)

@@ -105,6 +105,12 @@ class DistContext:
         self._step_gathers = 0
         self.peer_gathers = 0            # statistics: gathers served by gn_peer_allgather / by NCCL
         self.nccl_gathers = 0
+        self.peer_reductions = 0         # reductions served by gn_peer_push + gn_slot_sum / by NCCL
+        self.nccl_reductions = 0
+        # deferred mode: this rank's share of the global mean loss, summed over ranks (in rank order, together
+        # with the gradient bucket) by ``reduce_gradients`` into ``loss_value``
+        self._loss_share = None
+        self.loss_value = None
 
     # ---- block partition -------------------------------------------------
     def block(self, n):
@@ -180,6 +186,46 @@ class DistContext:
                     return t
         return torch.empty((rows, f), dtype=torch.float32, device=like.device)
 
+    def exchange_buffer(self, slot_bytes):
+        """A ``[world][slot_bytes]`` buffer of the symmetric arena for ``gn_peer_push`` / ``gn_slot_sum``
+        -> ``(uint8 view, arena offset, flag index)``, or None while the arena does not exist (first step,
+        peer mode off): the caller then uses NCCL.  Sizes are recorded like those of the gather buffers."""
+        slot_bytes = (int(slot_bytes) + 15) // 16 * 16
+        nbytes = slot_bytes * self.world
+        if self.peer_mode != "auto" or self.world == 1:
+            return None
+        self._step_bytes += (nbytes + 255) // 256 * 256
+        self._step_gathers += 1
+        if self.arena is None:
+            return None
+        tok = self.arena.alloc(nbytes)
+        return None if tok is None else tok + (slot_bytes,)
+
+    def _peer_push(self, tok, segments):
+        """``segments``: (tensor-or-pointer, bytes, slot_offset, peer or -1) -> one ``gn_peer_push``."""
+        from . import _lib
+        from .graph import _stream
+        a = self.arena
+        _, offset, index, slot_bytes = tok
+        table = (_lib.GnPeerSegment * len(segments))()
+        for i, (ptr, nbytes, off, peer) in enumerate(segments):
+            table[i] = _lib.GnPeerSegment(ptr, nbytes, off, peer)
+        _lib.check(_lib.load().gn_peer_push(a.bases, self.world, self.rank, offset, slot_bytes,
+                                            ctypes.cast(table, ctypes.c_void_p), len(segments), 0, index,
+                                            a.seq[index:].data_ptr(), a.done[index:].data_ptr(), a.abort.data_ptr(),
+                                            _stream()), "gn_peer_push")
+
+    def _slot_sum(self, tok, segments):
+        """``segments``: (dst tensor, n floats, slot_offset) -> one ``gn_slot_sum`` over this rank's buffer."""
+        from . import _lib
+        from .graph import _stream
+        view, _, _, slot_bytes = tok
+        table = (_lib.GnSumSegment * len(segments))()
+        for i, (dst, n, off) in enumerate(segments):
+            table[i] = _lib.GnSumSegment(dst.data_ptr(), n, off)
+        _lib.check(_lib.load().gn_slot_sum(view.data_ptr(), self.world, slot_bytes, ctypes.cast(table, ctypes.c_void_p),
+                                           len(segments), _stream()), "gn_slot_sum")
+
     # ---- collectives -----------------------------------------------------
     def all_gather_slots(self, full):
         """``full`` is ``[world*B, F]`` with this rank's slot already written: complete it in place —
@@ -215,27 +261,74 @@ class DistContext:
         return t
 
     def reduce_gradients(self, params):
-        """Bucketed all-reduce of the ``.grad`` of replicated parameters (``defer_grad_reduce=True``):
-        pack -> one all-reduce -> unpack.  ``params`` must not contain row-partitioned parameters."""
+        """All-reduce of the ``.grad`` of replicated parameters left as partial sums by a
+        ``defer_grad_reduce=True`` step, together with this rank's share of the loss (``global_mean_loss``):
+        every rank stores its gradients into slot ``rank`` of every rank's exchange buffer over NVLink peer
+        memory (``gn_peer_push``), then sums the slots in rank order straight back into the ``.grad`` tensors
+        (``gn_slot_sum``) — two launches, no NCCL, bit-identical results on every rank.  While the symmetric
+        arena does not exist (first step, or peer mode off) one bucketed NCCL all-reduce does the same.
+        ``params`` must not contain row-partitioned parameters."""
         if self.world == 1:
+            if self._loss_share is not None:
+                self.loss_value, self._loss_share = self._loss_share, None
             return
         grads = [p.grad for p in params if p.grad is not None]
-        if not grads:
+        share, self._loss_share = self._loss_share, None
+        if not grads and share is None:
             return
-        sizes = [g.numel() for g in grads]
-        if self._bucket is None or self._bucket.numel() != sum(sizes) or self._bucket.device != grads[0].device:
-            self._bucket = torch.empty(sum(sizes), dtype=grads[0].dtype, device=grads[0].device)
-        torch.cat([g.reshape(-1) for g in grads], out=self._bucket)
+        if any(not g.is_contiguous() for g in grads):
+            raise RuntimeError("gripnet_b200: gradients of replicated parameters must be contiguous")
+        pieces = list(grads)
+        if share is not None:
+            if self.loss_value is None or self.loss_value.device != share.device:
+                self.loss_value = torch.zeros(1, dtype=torch.float32, device=share.device)
+            pieces.append(share.view(1))
+        cuda = pieces[0].is_cuda
+        offs, off = [], 0
+        for t in pieces:
+            offs.append(off)
+            off += (t.numel() * 4 + 15) // 16 * 16
+        tok = self.exchange_buffer(off) if cuda and len(pieces) <= self._max_segments() else None
+        if tok is not None:
+            self._peer_push(tok, [(t.data_ptr(), t.numel() * 4, o, -1) for t, o in zip(pieces, offs)])
+            dsts = list(grads) + ([self.loss_value] if share is not None else [])
+            self._slot_sum(tok, [(d, d.numel(), o) for d, o in zip(dsts, offs)])
+            self.peer_reductions += 1
+            return
+        sizes = [t.numel() for t in pieces]
+        if self._bucket is None or self._bucket.numel() != sum(sizes) or self._bucket.device != pieces[0].device:
+            self._bucket = torch.empty(sum(sizes), dtype=pieces[0].dtype, device=pieces[0].device)
+        torch.cat([t.reshape(-1) for t in pieces], out=self._bucket)
         dist.all_reduce(self._bucket, op=dist.ReduceOp.SUM, group=self.group)
-        torch._foreach_copy_([g.view(-1) for g in grads], list(self._bucket.split(sizes)))
+        parts = list(self._bucket.split(sizes))
+        torch._foreach_copy_([g.view(-1) for g in grads], parts[: len(grads)])
+        if share is not None:
+            self.loss_value.copy_(parts[-1])
+        self.nccl_reductions += 1
+
+    def _max_segments(self):
+        from . import _lib
+        return int(_lib.load().gn_peer_max_segments())
 
     def reduce_scatter_rows(self, full):
-        """Sum ``full`` ``[world*B, F]`` over ranks and return this rank's ``[B, F]`` block."""
+        """Sum ``full`` ``[world*B, F]`` over ranks and return this rank's ``[B, F]`` block: block q of every
+        rank is stored into rank q's exchange buffer over peer memory (an all-to-all, ``gn_peer_push``) and the
+        ``world`` contributions are summed in rank order (``gn_slot_sum``); NCCL reduce-scatter as fallback."""
         b = full.size(0) // self.world
         if self.world == 1:
             return full[:b]
+        full = full.contiguous()
         out = torch.empty((b,) + tuple(full.shape[1:]), dtype=full.dtype, device=full.device)
-        dist.reduce_scatter_tensor(out, full.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
+        blk_bytes = out.numel() * 4
+        tok = self.exchange_buffer(blk_bytes) if (full.is_cuda and full.dtype == torch.float32 and
+                                                  self.world <= self._max_segments()) else None
+        if tok is not None:
+            self._peer_push(tok, [(full.data_ptr() + q * blk_bytes, blk_bytes, 0, q) for q in range(self.world)])
+            self._slot_sum(tok, [(out, out.numel(), 0)])
+            self.peer_reductions += 1
+            return out
+        dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.group)
+        self.nccl_reductions += 1
         return out
 
 
@@ -254,10 +347,11 @@ def block_bounds(n, world, rank):
 # the tensor alive so its storage cannot be recycled under a stale key)
 # --------------------------------------------------------------------------
 class EdgeSpec:
-    __slots__ = ("tensor", "ctx", "n_src", "n_dst")
+    __slots__ = ("tensor", "ctx", "n_src", "n_dst", "shards", "n_edges_global")
 
-    def __init__(self, tensor, ctx, n_src, n_dst):
+    def __init__(self, tensor, ctx, n_src, n_dst, shards=None, n_edges_global=None):
         self.tensor, self.ctx, self.n_src, self.n_dst = tensor, ctx, int(n_src), int(n_dst)
+        self.shards, self.n_edges_global = shards, n_edges_global
 
 
 _registry = {}
@@ -274,6 +368,18 @@ def distribute_edges(edge_index, ctx, n_src, n_dst=None):
     partitioned path and expect / return LOCAL rows."""
     _registry[_key(edge_index)] = EdgeSpec(edge_index, ctx, n_src, n_src if n_dst is None else n_dst)
     return edge_index
+
+
+def distribute_edge_shards(by_dst, by_src, ctx, n_src, n_dst=None, n_edges_global=None, w_dst=None, w_src=None):
+    """Register THIS RANK'S shard of a destination-partitioned edge list, for supergraphs whose global edge
+    list no rank should hold: ``by_dst`` = the edges (global ids, original relative order) whose destination
+    lies in this rank's block, ``by_src`` = those whose source does (``graph.filter_edges`` of a streamed
+    generator or loader gives both).  Returns the key tensor to pass as ``edge_index`` to the modules."""
+    n_dst = n_src if n_dst is None else n_dst
+    total = n_edges_global if n_edges_global is not None else by_dst.size(1)
+    _registry[_key(by_dst)] = EdgeSpec(by_dst, ctx, n_src, n_dst, shards=((by_dst, w_dst), (by_src, w_src)),
+                                       n_edges_global=total)
+    return by_dst
 
 
 def lookup(edge_index):
@@ -294,10 +400,17 @@ class AllGatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z_local, dctx, n_global):
         b = dctx.block(n_global)
-        full = torch.zeros((dctx.world * b, z_local.size(1)), dtype=z_local.dtype, device=z_local.device) \
-            if z_local.size(0) != b else \
-            torch.empty((dctx.world * b, z_local.size(1)), dtype=z_local.dtype, device=z_local.device)
-        full[dctx.rank * b: dctx.rank * b + z_local.size(0)].copy_(z_local)
+        if z_local.is_cuda:
+            # gather buffer from the symmetric arena; the local rows are placed by a library copy kernel.
+            # Rows past n (padding of the last block) are never indexed by an edge list.
+            from . import _lib, ops
+            full = dctx.slot_buffer(dctx.world * b, z_local.size(1), z_local)
+            if z_local.size(0) > 0:
+                ops.map2d(_lib.EW_COPY, ops.M(ops._as_rows(z_local, "z")),
+                          ops.M(full[dctx.rank * b: dctx.rank * b + z_local.size(0)]))
+        else:                                           # gloo host tests (CPU tensors): plumbing only
+            full = torch.zeros((dctx.world * b, z_local.size(1)), dtype=z_local.dtype, device=z_local.device)
+            full[dctx.rank * b: dctx.rank * b + z_local.size(0)].copy_(z_local)
         dctx.all_gather_slots(full)
         ctx.dctx, ctx.n_local = dctx, z_local.size(0)
         return full
@@ -350,5 +463,36 @@ class _ScaleAllReduceLoss(torch.autograd.Function):
         return g * ctx.weight, None, None
 
 
+class _LossShare(torch.autograd.Function):
+    """``w_p * loss_p`` by a library kernel (deferred mode: the sum over ranks is formed later, with the
+    gradient bucket, by ``DistContext.reduce_gradients``)."""
+
+    @staticmethod
+    def forward(ctx, loss_local, weight):
+        from . import ops
+        ctx.weight = float(weight)
+        out = torch.empty(1, dtype=torch.float32, device=loss_local.device)
+        ops.axpby(ops.M(loss_local.detach().view(1, 1)), ctx.weight, None, 0.0, ops.M(out.view(1, 1)))
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import ops
+        out = torch.empty(1, dtype=torch.float32, device=g.device)
+        ops.axpby(ops.M(g.contiguous().view(1, 1)), ctx.weight, None, 0.0, ops.M(out.view(1, 1)))
+        return out.view(()), None
+
+
 def global_mean_loss(loss_local, n_local, n_global, dctx):
-    return _ScaleAllReduceLoss.apply(loss_local, float(n_local) / float(n_global), dctx)
+    """Global mean of a per-sample loss from this rank's mean over its ``n_local`` samples.
+
+    ``defer_grad_reduce=False``: the value is all-reduced here (NCCL) and returned.
+    ``defer_grad_reduce=True`` (CUDA): returns THIS RANK'S SHARE ``n_local / n_global * loss_local`` — its
+    backward is exactly the global loss's — and parks it for ``reduce_gradients``, which sums the shares in
+    rank order into ``dctx.loss_value`` with the same exchange that reduces the weight gradients."""
+    w = float(n_local) / float(n_global)
+    if dctx.defer_grad_reduce and loss_local.is_cuda:
+        share = _LossShare.apply(loss_local, w)
+        dctx._loss_share = share.detach()
+        return share
+    return _ScaleAllReduceLoss.apply(loss_local, w, dctx)

@@ -12,6 +12,7 @@ from torch.nn import Module, Parameter
 
 from . import parallel
 from .decoder import multiClassInnerProductDecoder, multiRelaInnerProductDecoder
+from . import ops
 from .layers import homoGraph, interGraph
 from .losses import link_prediction_loss, node_classification_loss
 
@@ -35,7 +36,9 @@ class PoseModel(Module):
         """Returns (loss, z, pos_score, neg_score) for one training step's forward.
 
         Partitioned run (``data`` from ``shard_pose``): ``z`` holds this rank's drug rows, the scores
-        are those of this rank's slice of the edge lists, the loss is the global mean."""
+        are those of this rank's slice of the edge lists, the loss is the global mean — or, with
+        ``DistContext(defer_grad_reduce=True)``, this rank's SHARE of it (same backward); the global value
+        is then in ``dctx.loss_value`` after ``dctx.reduce_gradients(...)``."""
         dctx = data.get("dist")
         if dctx is not None:
             dctx.begin_step()
@@ -46,8 +49,8 @@ class PoseModel(Module):
             return link_prediction_loss(pos_score, neg_score), z, pos_score, neg_score
         neg = data["neg_edge_index_local"] if neg_edge_index is None else neg_edge_index
         z_full = parallel.all_gather_rows(z, dctx, data["n_d_global"])
-        pos_score = self.dmt(z_full, data["dd_edge_index_local"], data["dd_edge_type_local"])
-        neg_score = self.dmt(z_full, neg, data["dd_edge_type_local"])
+        pos_score, neg_score = self.dmt.score_pair(z_full, data["dd_edge_index_local"], neg,
+                                                   data["dd_edge_type_local"])
         loss = parallel.global_mean_loss(link_prediction_loss(pos_score, neg_score), pos_score.numel(),
                                          data["e_dd_global"], dctx)
         return loss, z, pos_score, neg_score
@@ -86,7 +89,7 @@ class FreebaseDModel(Module):
                     if_relu=True)
         z1 = self.qa(self.qq(None, data["qq_edge_index"], if_catout=True), data["qa_edge_index"], mod="add",
                      if_relu=True)
-        z = self.aa((z + z1 + self.aa_embeddings) / 3, data["aa_edge_index"])       # freebase-d.py:160-164
+        z = self.aa(ops.mean3(z, z1, self.aa_embeddings), data["aa_edge_index"])    # freebase-d.py:160-164
         score = self.mcip(z, data["train_node_idx"])
         return node_classification_loss(score, data["train_node_class"]), z, score
 
@@ -123,8 +126,10 @@ class ChainModel(Module):
 
 def chain_edges_per_epoch(g):
     """Input edges traversed by one forward of ``ChainModel`` (2 GCN layers per supervertex)."""
-    return (2 * g["aa_edge_index"].shape[1] + g["ab_edge_index"].shape[1] + 2 * g["bb_edge_index"].shape[1]
-            + g["bc_edge_index"].shape[1] + 2 * g["cc_edge_index"].shape[1])
+    c = g.get("edge_counts")
+    if c is None:
+        c = {k: g[k + "_edge_index"].shape[1] for k in ("aa", "ab", "bb", "bc", "cc")}
+    return 2 * c["aa"] + c["ab"] + 2 * c["bb"] + c["bc"] + 2 * c["cc"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -176,6 +181,46 @@ def shard_chain(g, dctx, device):
     mine = ((idx >= r0) & (idx < r1)).nonzero().view(-1)
     d.update({"dist": dctx, "n_train_global": int(idx.numel()),
               "n_a": dctx.local_count(n_a), "n_b": dctx.local_count(n_b), "n_c": r1 - r0,
+              "train_node_idx": (idx[mine] - r0).contiguous(), "train_node_class": cls[mine].contiguous()})
+    return d
+
+
+def shard_chain_streamed(make_graph, dctx, device):
+    """Per-rank ``data`` dict for ``ChainModel`` WITHOUT any rank holding a global edge list: ``make_graph``
+    (``synthdata.chain_full`` / ``chain_small``) streams every intra-supervertex graph chunk by chunk through
+    sinks that keep only the edges touching this rank's block (``graph.filter_edges``) and registers the two
+    shards (by destination -> forward CSR rows, by source -> transpose CSR rows) with
+    ``parallel.distribute_edge_shards``.  Every rank consumes the generator's random stream identically, so the
+    union of the shards is exactly the graph the single-GPU run sees."""
+    from .graph import filter_edges
+
+    def homo_sink(name, n, e_directed, half_chunks):
+        r0, r1 = dctx.bounds(n)
+        a_parts, b_parts = [], []
+        for chunk in half_chunks:                          # global list = [half, flip(half)]
+            a_parts.append(filter_edges(chunk, None, False, r0, r1)[0])      # half, destination in the block
+            b_parts.append(filter_edges(chunk, None, True, r0, r1)[0])       # half, source in the block
+            del chunk
+        a, b = torch.cat(a_parts, dim=1), torch.cat(b_parts, dim=1)
+        by_dst = torch.cat([a, b.flip(0)], dim=1).contiguous()
+        by_src = torch.cat([b, a.flip(0)], dim=1).contiguous()
+        return parallel.distribute_edge_shards(by_dst, by_src, dctx, n, n, n_edges_global=e_directed)
+
+    def bip_sink(name, ns, nt, ei):
+        s0, s1 = dctx.bounds(ns)
+        t0, t1 = dctx.bounds(nt)
+        by_dst = filter_edges(ei, None, False, t0, t1)[0].contiguous()
+        by_src = filter_edges(ei, None, True, s0, s1)[0].contiguous()
+        return parallel.distribute_edge_shards(by_dst, by_src, dctx, ns, nt, n_edges_global=ei.size(1))
+
+    g = make_graph(device, homo_sink=homo_sink, bip_sink=bip_sink)
+    n_a, n_b, n_c = g["n_a"], g["n_b"], g["n_c"]
+    r0, r1 = dctx.bounds(n_c)
+    idx, cls = g["train_node_idx"], g["train_node_class"]
+    mine = ((idx >= r0) & (idx < r1)).nonzero().view(-1)
+    d = dict(g)
+    d.update({"dist": dctx, "n_train_global": int(idx.numel()), "n_a_global": n_a, "n_b_global": n_b,
+              "n_c_global": n_c, "n_a": dctx.local_count(n_a), "n_b": dctx.local_count(n_b), "n_c": r1 - r0,
               "train_node_idx": (idx[mine] - r0).contiguous(), "train_node_class": cls[mine].contiguous()})
     return d
 

@@ -4,6 +4,9 @@ scripts call around the hot path (constants, range lists, negative sampling).
 These are data-preparation utilities: kept so a script
 written against ``gripnet.utils`` imports cleanly; they are not kernels.
 """
+import itertools
+from collections import OrderedDict
+
 import numpy as np
 import torch
 
@@ -101,25 +104,46 @@ class NegativeSampler:
                                                  _ptr(out[1]) if self.n_edges else None, _stream()),
                    "gn_negsample_draw")
         torch.autograd.graph.increment_version(out)      # written behind torch's back: structures cached per
-        return out                                       # (tensor, version) must be rebuilt for the new draw
+        from .graph import mark_valid                    # (tensor, version) must be rebuilt for the new draw
+        mark_valid(out, self.n_nodes)                    # in range by construction: no host check downstream
+        return out
 
     @property
     def epoch(self):
         return int(self.state[0].item())
 
 
-_samplers = {}
+_samplers = OrderedDict()
+_SAMPLER_CAPACITY = 64
+_sampler_births = itertools.count()
+
+
+def _fresh_seed():
+    """Seed of a sampler created by the functional API.  The reference draws fresh numpy randoms on every
+    call (utils.py:104-110), so two samplers must never share a stream: the seed mixes ``torch.initial_seed()``
+    (reproducible under ``torch.manual_seed``) with a process-wide birth counter through SplitMix64."""
+    x = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * (next(_sampler_births) + 1)) & (2 ** 64 - 1)
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+    return x ^ (x >> 31)
 
 
 def _sampler_for(pos_edge_index, num_nodes, range_list):
+    """Sampler cached per (edge tensor identity + version, num_nodes, range_list), LRU eviction.  A cache hit
+    continues that sampler's epoch sequence; a miss (a fresh clone or slice of the positives every call, or more
+    than ``_SAMPLER_CAPACITY`` live edge tensors) builds a new hash table AND a new, distinct random stream —
+    pass the SAME tensor every epoch to avoid the rebuild."""
     from .graph import _Cache
     key = (_Cache.tkey(pos_edge_index), int(num_nodes),
            None if range_list is None else tuple(torch.as_tensor(range_list).flatten().tolist()))
     hit = _samplers.get(key)
     if hit is None:
-        if len(_samplers) >= 8:
-            _samplers.pop(next(iter(_samplers)))
-        hit = _samplers[key] = (NegativeSampler(pos_edge_index, num_nodes, range_list), pos_edge_index)
+        while len(_samplers) >= _SAMPLER_CAPACITY:
+            _samplers.popitem(last=False)
+        hit = _samplers[key] = (NegativeSampler(pos_edge_index, num_nodes, range_list, seed=_fresh_seed()),
+                                pos_edge_index)
+    else:
+        _samplers.move_to_end(key)
     return hit[0]
 
 

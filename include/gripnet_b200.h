@@ -43,6 +43,10 @@ typedef enum {
 
 int gn_version(void);
 const char* gn_error_string(int status);
+/* cudaError_t (and its runtime text) of the most recent launch of this library that failed with
+ * GN_ERR_CUDA; 0 / "no error" when none has */
+int gn_last_cuda_error(void);
+const char* gn_last_cuda_error_string(void);
 /* number of kernels this library has launched in this process (monotonic) */
 uint64_t gn_launch_count(void);
 
@@ -114,6 +118,38 @@ int gn_gcn_prep(const int64_t* src, const int64_t* dst, const float* weight /*or
                 int32_t* rowptr_t, int32_t* col_t, float* val_t, int32_t* perm_t,
                 float* deg, int32_t* indeg, int32_t* counts,
                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K1 for destination-partitioned graphs (new design: the reference is single-device) ----
+ * Every rank builds only ITS rows of the dst-sorted CSR (forward) and of the src-sorted transpose CSR
+ * (backward); results are bit-identical to the matching rows of gn_gcn_prep's global CSR.
+ *
+ * gn_edge_filter: order-preserving selection of the edges whose destination (by_src == 0) or source
+ * (by_src != 0) lies in [lo, hi).  count (device int32) receives the number selected; with out_src ==
+ * NULL only the count is produced (size the outputs, then call again).  out_index (optional) receives
+ * index_base + original position.  n_edges < 2^31 per call: longer lists are filtered chunk by chunk. */
+size_t gn_edge_filter_workspace_bytes(int64_t n_edges);
+int gn_edge_filter(const int64_t* src, const int64_t* dst, const float* weight /*or NULL*/, int64_t n_edges,
+                   int by_src, int64_t lo, int64_t hi, int64_t* out_src, int64_t* out_dst,
+                   float* out_weight /*or NULL*/, int64_t* out_index /*or NULL*/, int64_t index_base,
+                   int32_t* count, void* ws, size_t ws_bytes, void* stream);
+/* gn_gcn_part_structure: rows [row0, row0 + n_rows) of the CSR keyed by `key_end` (destinations for the
+ * forward CSR, sources for the transpose) from a shard in which every key_end lies in that block;
+ * `other_end` ids are global.  with_loops: the self-loop rewrite of gripnet/layers.py:52-60 restricted to
+ * the block (loop entry = last slot of each row, column row0 + i, weight = that of the last listed
+ * self-loop or fill_value).  Outputs: rowptr [n_rows + 1], col / val [n_edges + n_rows] (val holds the
+ * per-entry WEIGHT), counts[0] = stored entries; dis / deg [n_rows] (dis != NULL): weighted in-degree in
+ * list order and its -1/2 power (inf -> 0) — meaningful for the destination-keyed build
+ * (with_loops == 0: the bipartite closed form, deg = 1 + sum w).
+ * gn_gcn_part_values: val <- (dis_src[source] * w) * dis_dst[target] (layers.py:66-69) with GLOBAL deg^-1/2
+ * vectors (all-gathered by the caller); dis_src == NULL means 1 (bipartite); transpose: rows are sources. */
+size_t gn_gcn_part_workspace_bytes(int64_t n_edges, int32_t n_rows);
+int gn_gcn_part_structure(const int64_t* key_end, const int64_t* other_end, const float* weight /*or NULL*/,
+                          int64_t n_edges, int32_t row0, int32_t n_rows, int with_loops, float fill_value,
+                          int32_t* rowptr, int32_t* col, float* val, float* deg /*or NULL*/, float* dis /*or NULL*/,
+                          int32_t* counts, void* ws, size_t ws_bytes, void* stream);
+int gn_gcn_part_values(const int32_t* rowptr, const int32_t* col, int32_t n_rows, int32_t row0,
+                       const float* dis_src /*or NULL*/, const float* dis_dst, int transpose, float* val,
+                       void* stream);
 
 /* Multi-relational prep.  Replaces the structure implied by gripnet/layers.py:165-189
  * (relation of edge e = index of the range_list slice containing e; edge_type unused)
@@ -192,6 +228,16 @@ int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const float* A, int6
                const float* addend, int64_t ld_addend, const float* relu_mask, int64_t ld_mask,
                void* ws, size_t ws_bytes, void* stream);
 
+/* Relation-batched feature transform of myRGCN on the tensor cores (north_star item 3):
+ *   Y[:, r, :] = X W[r] for all r  ==  Y[M, n_rel*f] = X[M, K] . W_flat[K, n_rel*f],   W stored [n_rel][K][f]
+ * (gripnet/layers.py:171-189 evaluates matmul(x_j[s:e], w[et]) per EDGE; here it is once per node and
+ * relation, then the segmented SpMM gathers rows of Y).  Same 3xTF32 kernel and accuracy as gn_tc_gemm; the
+ * shared-memory image of W_flat is built straight from the [n_rel][K][f] layout into `ws`
+ * (gn_tc_gemm_rel_workspace_bytes).  Requirements: X / Y 16-byte aligned, ldx, ldy, K multiples of 4. */
+size_t gn_tc_gemm_rel_workspace_bytes(int32_t M, int32_t n_rel, int32_t f, int32_t K);
+int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
+                   const float* W, float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K9/K10: DistMult decoder  ------------------------------------------- */
 /* score_e = sum_k z[src_e,k] z[dst_e,k] w[rel_e,k]; sigmoid optional.
  * Replaces gripnet/decoder.py:19-23 (three [E,D] gathers + two muls + sum). */
@@ -211,41 +257,25 @@ int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64
                       const int64_t* dst, const float* coef, const float* z, int64_t ldz,
                       int32_t D, float* dw, float* partial, void* stream);
 
-/* K9/K10 with the embedding table RESIDENT in shared memory: the decoder scores edges inside the task
- * supervertex, whose table is small (645 x 80 floats = 206 KB on every pose dataset) — when
- * n_nodes * D * 4 <= 227 KB (gn_distmult_resident_ok) one persistent CTA per SM copies z into shared memory once
- * and every row gather of the three kernels is a conflict-free shared-memory read instead of an L1 lookup.
- * Same arguments, results and determinism as the calls above (the forward also takes n_nodes, the weight
- * gradient n_nodes); requires D % 4 == 0, ldz % 4 == 0 and 16-byte aligned z / w / outputs. */
-int gn_distmult_resident_ok(int64_t n_nodes, int32_t D, int64_t ldz);
-int gn_distmult_fwd_resident(const float* z, int64_t ldz, int32_t n_nodes, int32_t D, const float* w,
-                             const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges,
-                             int sigmoid, float* out, void* stream);
-int gn_distmult_bwd_z_resident(const gn_csr* node_csr, const int32_t* ent_other, const int32_t* ent_rel,
-                               const int32_t* ent_eid, const float* coef, const float* z, int64_t ldz, int32_t D,
-                               const float* w, float* dz, int64_t lddz, float* partial, void* stream);
-int gn_distmult_bwd_w_resident(const gn_csr* rel_csr, const int32_t* rel_eid, const int64_t* src,
-                               const int64_t* dst, const float* coef, const float* z, int64_t ldz, int32_t n_nodes,
-                               int32_t D, float* dw, float* partial, void* stream);
-
-/* K9/K10 in DENSE-RELATION form — EXPERIMENTAL (parity-checked on a B200, not yet timed, off by default).  For a small task supervertex with dense relation slices (pose: 645 nodes, 6 % of the node pairs per
- * relation) the decoder is R batched dense products plus one 4-byte gather per edge instead of row gathers:
- *   forward : zw[r] = z .* w[r] (gn_distmult_dense_scale), S[r] = zw[r] z^T (gn_sgemm, batch R),
- *             score_e = act(S[rel_e][src_e][dst_e]) (gn_distmult_dense_scores)
- *   backward: C[r][n][m] = sum of coef_e over the edges of relation r joining n and m, accumulated from the
- *             endpoint CSR in entry order by one warp per node row (gn_distmult_dense_coef; zero_first clears C,
- *             a second call adds another edge list), T[r] = C[r] z (gn_sgemm, batch R),
- *             dz = sum_r T[r] .* w[r], dw[r] = 1/2 sum_n z[n] .* T[r][n] (gn_distmult_dense_grads).
- * zw, T: [n_rel][n_nodes][D]; S, C: [n_rel][n_nodes][n_nodes]; all dense fp32, caller-owned. */
-int gn_distmult_dense_scale(const float* z, int64_t ldz, int32_t n_nodes, int32_t D, const float* w,
-                            int32_t n_rel, float* zw, void* stream);
-int gn_distmult_dense_scores(const float* S, int32_t n_nodes, const int64_t* src, const int64_t* dst,
-                             const int64_t* etype, int64_t n_edges, int sigmoid, float* out, void* stream);
-int gn_distmult_dense_coef(const int32_t* node_rowptr, const int32_t* ent_other, const int32_t* ent_rel,
-                           const int32_t* ent_eid, const float* coef, int32_t n_nodes, int32_t n_rel,
-                           int zero_first, float* C, void* stream);
-int gn_distmult_dense_grads(const float* T, int32_t n_nodes, int32_t D, int32_t n_rel, const float* z, int64_t ldz,
-                            const float* w, float* dz, int64_t lddz, float* dw, void* stream);
+/* K10 in ONE gather pass.  gn_pair_prep groups the 2E endpoint entries of an edge list by (node, relation):
+ * pair_rowptr [n_nodes * n_rel + 1] (row = node * n_rel + rel), entries (other endpoint, edge id) in their
+ * original relative order (stable sort).  gn_distmult_bwd_pairs walks it once:
+ *   T[n, r, :] = sum over the entries of pair row (n, r) of coef[e] * z[other]      (T: [n_nodes*n_rel, D])
+ * and gn_distmult_grads finishes both gradients from T (plus an optional second T2 of another edge list,
+ * e.g. the negatives of the same step) without touching the edges again:
+ *   dz[n] = sum_r T[n,r] .* w[r],      dw[r] = 1/2 sum_n z[n] .* T[n,r]
+ * (every edge sits in the pair rows of both of its endpoints, hence the 1/2).  Replaces the autograd of
+ * gripnet/decoder.py:19-23 (three index_put scatters); atomic-free, fixed summation order. */
+size_t gn_pair_prep_workspace_bytes(int64_t n_edges);
+int gn_pair_prep(const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges, int32_t n_nodes,
+                 int32_t n_rel, int32_t* pair_rowptr, int32_t* ent_other, int32_t* ent_eid /*[2E]*/,
+                 void* ws, size_t ws_bytes, void* stream);
+int gn_distmult_bwd_pairs(const gn_csr* pair_csr, const int32_t* ent_other, const int32_t* ent_eid,
+                          const float* coef, const float* z, int64_t ldz, int32_t D, float* T, float* partial,
+                          void* stream);
+int gn_distmult_grads(const float* T, const float* T2 /*or NULL*/, int32_t n_nodes, int32_t n_rel, int32_t D,
+                      const float* z, int64_t ldz, const float* w, float* dz /*or NULL*/, int64_t lddz,
+                      float* dw /*or NULL*/, void* stream);
 
 /* ---- K11: multi-class decoder pieces  ------------------------------------ */
 /* row softmax over C columns (gripnet/decoder.py:43) and its backward */
@@ -267,6 +297,10 @@ int gn_abs_bwd(const float* g, int64_t ldg, const float* t, int64_t ldt, float* 
 /* dst = alpha * a + beta * b  (b may be NULL; dst may alias a or b)
  * — the (x + u) / 2 mixes of interGraph, layers.py:379/382-384 */
 int gn_axpby(const float* a, int64_t lda, float alpha, const float* b, int64_t ldb, float beta,
+             float* dst, int64_t ldd, int64_t n, int32_t F, void* stream);
+/* dst = ((a + b) + c) / 3 — the three-way mix of the freebase-d model, GripNet-freebase-d.py:160-161
+ * (same association order, true division) */
+int gn_mean3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc,
              float* dst, int64_t ldd, int64_t n, int32_t F, void* stream);
 /* out[0:F] = sum_i x[i, 0:F], deterministic two-level reduction; ws >= gn_colsum_workspace_bytes */
 size_t gn_colsum_workspace_bytes(int64_t n, int32_t F);
@@ -366,6 +400,37 @@ int gn_peer_max_world(void);
 int gn_peer_allgather(const uint64_t* arena_base /*host*/, int32_t world, int32_t rank, int64_t buf_offset,
                       int64_t slot_bytes, int64_t flag_offset, int32_t flag_index, uint64_t* seq,
                       uint32_t* done, uint32_t* abort_flag, void* stream);
+
+
+/* Segmented push + rank-ordered sum over the same arena: the small reductions of a partitioned step
+ * (bucketed weight-gradient all-reduce + loss, reduce-scatter of the decoder's dz) without NCCL.
+ * The exchange buffer is [world][slot_bytes] at `buf_offset` of every arena.  gn_peer_push stores every
+ * segment into slot `rank` of the buffer of its target rank (`peer` >= 0) or of EVERY rank incl. this one
+ * (`peer` < 0), at `slot_offset` inside the slot, then runs the publish / wait round of gn_peer_allgather
+ * (same flag / seq / done / abort arguments).  `segs` is a HOST array (the descriptors travel in the
+ * kernel-parameter block: capturable), at most gn_peer_max_segments() entries; bytes and offsets are
+ * multiples of 4 (128-bit copies when everything is 16-byte aligned).
+ * gn_slot_sum then forms dst[i] = slot_0[i] + slot_1[i] + ... + slot_{world-1}[i] IN RANK ORDER from this
+ * rank's own buffer (`buf` = local arena base + buf_offset): every rank adds the same numbers in the same
+ * order, so replicated gradients stay bit-identical across ranks and run to run. */
+typedef struct {
+  const void* src;      /* device pointer (any local memory) */
+  int64_t bytes;
+  int64_t slot_offset;  /* byte offset inside the slot */
+  int32_t peer;         /* target rank, or < 0 for every rank */
+} gn_peer_segment;
+typedef struct {
+  float* dst;           /* device pointer, n floats */
+  int64_t n;
+  int64_t slot_offset;  /* byte offset inside the slot */
+} gn_sum_segment;
+int gn_peer_max_segments(void);
+int gn_peer_push(const uint64_t* arena_base /*host*/, int32_t world, int32_t rank, int64_t buf_offset,
+                 int64_t slot_bytes, const gn_peer_segment* segs /*host*/, int32_t n_segs,
+                 int64_t flag_offset, int32_t flag_index, uint64_t* seq, uint32_t* done, uint32_t* abort_flag,
+                 void* stream);
+int gn_slot_sum(const void* buf, int32_t world, int64_t slot_bytes, const gn_sum_segment* segs /*host*/,
+                int32_t n_segs, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,14 +1,14 @@
 """Parameter sets + re-exported synthetic supergraphs for the oracle / tests.
 
 TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  The graph generators live in
-``gripnet_b200/synthetic.py`` (the benchmark's own arm needs them and may not import
-``oracle/``); this module adds parameter dictionaries drawn from the reference's
+the neutral top-level ``synthdata`` module (the benchmark's own arm needs them and may not import
+``oracle/``; the reference arm and this package may not import the product); this module adds parameter dictionaries drawn from the reference's
 initial distributions under the reference's ``state_dict`` names.
 """
 import numpy as np
 import torch
 
-from gripnet_b200.synthetic import (  # noqa: F401
+from synthdata import (  # noqa: F401
     aminer_full, aminer_small, freebase_d_full, freebase_d_small, nc_graph, pose2_graph, pose2_rel_sizes,
     pose_edges_per_epoch, pose_graph, pose_medium, pose_small)
 

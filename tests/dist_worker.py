@@ -54,8 +54,9 @@ def run_pose(dctx, dev, with_oracle):
     m.dmt.dist_ctx = dctx
     loss, z, pos, neg = m(data)
     loss.backward()
-    if dctx.defer_grad_reduce:          # partial sums in .grad until the bucketed all-reduce
+    if dctx.defer_grad_reduce:          # partial sums in .grad (and this rank's loss share) until the reduction
         dctx.reduce_gradients([v for k, v in m.named_parameters() if k not in ("gg.embedding", "gd.target_feat")])
+        loss = dctx.loss_value.view(())
     worst = 0.0
     r0, r1 = dctx.bounds(g["n_d"])
     e0, e1 = data["edge_slice"]
@@ -80,17 +81,19 @@ def run_pose(dctx, dev, with_oracle):
     return worst
 
 
-def run_chain(dctx, dev):
+def run_chain(dctx, dev, streamed=False):
+    """``streamed``: every rank keeps only its shard of each generated chunk (no global edge list, no global
+    CSR on any rank) — the way bench.py builds BASELINE config 5."""
     from gripnet_b200 import graph as G
-    from gripnet_b200.pipelines import ROW_PARTITIONED, ChainModel, shard_chain
-    from gripnet_b200.synthetic import chain_small
+    from gripnet_b200.pipelines import ROW_PARTITIONED, ChainModel, shard_chain, shard_chain_streamed
+    from synthdata import chain_small
     g = chain_small(dev)
     torch.manual_seed(5)
     ref = ChainModel(g["n_a"], g["n_b"], g["n_c"], g["n_class"], hid=16, out=8).to(dev)
     loss_g, z_g, _ = ref(g)
     loss_g.backward()
     G.clear_cache()
-    data = shard_chain(g, dctx, dev)
+    data = shard_chain_streamed(chain_small, dctx, dev) if streamed else shard_chain(g, dctx, dev)
     m = ChainModel(data["n_a"], data["n_b"], data["n_c"], g["n_class"], hid=16, out=8).to(dev)
     m.mcip.dist_ctx = dctx
     sd = {}
@@ -114,10 +117,11 @@ def run_chain(dctx, dev):
 
 
 def run_peer(dctx, dev):
-    """Peer-memory exchange (gn_peer_allgather over the symmetric arena) against the NCCL exchange:
-    step 1 runs on NCCL (the arena is sized from it), steps 2.. push slots over NVLink peer memory.
-    The gather is a copy and every kernel is deterministic, so all steps must agree BIT FOR BIT —
-    eagerly and when the step is replayed from a CUDA graph."""
+    """Peer-memory exchange (gn_peer_allgather / gn_peer_push + gn_slot_sum over the symmetric arena) against
+    the NCCL exchange: step 1 runs on NCCL (the arena is sized from it), steps 2.. move everything over NVLink
+    peer memory.  Gathers are copies and every kernel is deterministic, so forward results must agree BIT FOR
+    BIT; reductions are summed in rank order instead of NCCL's order, so gradients agree to rounding (1e-6) —
+    and bit for bit between two peer-memory steps, eagerly and when the step is replayed from a CUDA graph."""
     from gripnet_b200 import graph as G
     from gripnet_b200.capture import CapturedStep
     from gripnet_b200.pipelines import PoseModel, load_flat_params, shard_pose, shard_pose_params
@@ -128,30 +132,45 @@ def run_peer(dctx, dev):
     data = shard_pose(g, dctx, dev)
     m = load_flat_params(PoseModel(data["n_g"], data["n_d"], g["n_rel"]), shard_pose_params(p, g, dctx)).to(dev)
     m.dmt.dist_ctx = dctx
+    replicated = [v for k, v in m.named_parameters() if k not in ("gg.embedding", "gd.target_feat")]
+
+    def finish():
+        if dctx.defer_grad_reduce:
+            dctx.reduce_gradients(replicated)
+
+    def loss_of(out):
+        return (dctx.loss_value if dctx.defer_grad_reduce else out[0]).detach().clone().view(())
+
     snaps = []
     side = torch.cuda.Stream()           # not the legacy stream: the same model is captured below
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        for step in range(3):
+        for step in range(4):
             m.zero_grad(set_to_none=True)
-            loss, z, pos, neg = m(data)
-            loss.backward()
+            out = m(data)
+            out[0].backward()
+            finish()
             torch.cuda.synchronize()
-            snaps.append([loss.detach().clone(), z.detach().clone()] +
+            snaps.append([loss_of(out), out[1].detach().clone()] +
                          [v.grad.clone() for v in m.parameters() if v.grad is not None])
     torch.cuda.synchronize()
     used_peer = dctx.peer_gathers > 0
     assert not dctx.peer_failed(), "a peer gather timed out"
+    assert torch.equal(snaps[0][1], snaps[2][1]), "peer-memory gather differs from the NCCL gather"
     for a, b in zip(snaps[0], snaps[2]):
-        assert torch.equal(a, b), "peer-memory exchange differs from the NCCL exchange"
+        check("peer vs nccl", a, b, 1e-6)
+    for a, b in zip(snaps[2], snaps[3]):
+        assert torch.equal(a, b), "two peer-memory steps differ"
     # captured + replayed
-    step = CapturedStep(lambda: m(data), m.parameters(), warmup=1)
+    step = CapturedStep(lambda: m(data), m.parameters(), warmup=1, post_backward=finish)
     for _ in range(3):
         out = step.replay()
     torch.cuda.synchronize()
     assert not dctx.peer_failed()
-    assert torch.equal(out[0].detach(), snaps[0][0]) and torch.equal(out[1].detach(), snaps[0][1])
-    return used_peer, dctx.peer_gathers, dctx.nccl_gathers
+    assert torch.equal(loss_of(out), snaps[2][0]) and torch.equal(out[1].detach(), snaps[2][1])
+    for a, b in zip([v.grad for v in m.parameters() if v.grad is not None], snaps[2][2:]):
+        assert torch.equal(a, b), "replayed gradients differ from the eager peer-memory step"
+    return used_peer, dctx.peer_gathers, dctx.nccl_gathers, dctx.peer_reductions, dctx.nccl_reductions
 
 
 def main():
@@ -168,16 +187,18 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     dctx = DistContext()
     w1 = run_pose(dctx, dev, with_oracle=(rank == 0))
-    w2 = run_chain(dctx, dev)
+    w2 = max(run_chain(dctx, dev), run_chain(dctx, dev, streamed=True))
     w1 = max(w1, run_pose(DistContext(defer_grad_reduce=True), dev, with_oracle=False))
-    peer = (False, 0, 0)
+    peer = (False, 0, 0, 0, 0)
     if world > 1:
-        peer = run_peer(DistContext(), dev)
+        run_peer(DistContext(), dev)
+        peer = run_peer(DistContext(defer_grad_reduce=True), dev)
     t = torch.tensor([w1, w2], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(f"dist_worker: world={world} OK  worst rel err pose {float(t[0]):.2e}  chain {float(t[1]):.2e}  "
-              f"peer-memory exchange {'ON' if peer[0] else 'off'} ({peer[1]} peer / {peer[2]} nccl gathers)", flush=True)
+              f"peer-memory exchange {'ON' if peer[0] else 'off'} ({peer[1]} peer / {peer[2]} nccl gathers, "
+              f"{peer[3]} peer / {peer[4]} nccl reductions)", flush=True)
     torch.cuda.synchronize()
     dist.barrier()
     sys.stdout.flush()

@@ -1,5 +1,6 @@
-"""GPU: destination-partitioned path (parallel.py).  world=1 runs in every `-m gpu` session; world=2
-needs two visible GPUs (gpurun --gpus 2) and is skipped otherwise."""
+"""GPU: destination-partitioned path (parallel.py).  world=1 runs in every `-m gpu` session; world=2/4/8
+need that many visible GPUs (gpurun --gpus N) and are skipped otherwise; the logs of the builder's own
+multi-GPU runs are under profiles/ (r02_*_pytest_dist_n*.txt)."""
 import os
 import subprocess
 import sys
@@ -28,7 +29,7 @@ def test_partitioned_world1_equals_single_gpu():
     _run(1, 29551)
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_multi_gpu_equals_single_gpu(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -147,16 +147,7 @@ def test_sgemm_epilogue_batch_and_gather():
     assert rel_err(dX, np.einsum("mrn,rkn->mk", Y.cpu().numpy().astype(np.float64), W)) < TOL
 
 
-@pytest.fixture(params=["auto", "global"])
-def decoder_path(request, monkeypatch):
-    """Both decoder kernel families: "auto" = table resident in shared memory where it fits (decoder_resident.cu),
-    "global" = the global-memory gather kernels (decoder.cu) for every shape."""
-    from gripnet_b200 import ops
-    monkeypatch.setattr(ops, "DECODER_PATH", request.param)
-    return request.param
-
-
-def test_distmult_forward_backward(decoder_path):
+def test_distmult_forward_backward():
     from gripnet_b200 import ops
     rs = np.random.RandomState(2)
     d = _dev()
@@ -182,9 +173,10 @@ def test_distmult_forward_backward(decoder_path):
 
 
 @pytest.mark.parametrize("n", [645, 3000])
-def test_distmult_pose_sized_and_pair(n, decoder_path):
+def test_distmult_pose_sized_and_pair(n):
     """Pose-sized decoder call (n = 645 drugs x D = 80, 400 k edges) and a larger table, against float64;
-    the fused pos/neg pair against two single calls (bit-identical)."""
+    the fused pos/neg pair against two single calls (scores bit-identical; the pair adds the two lists' T
+    before the products with w / z, two single calls add afterwards: gradients agree to rounding)."""
     from gripnet_b200 import ops
     rs = np.random.RandomState(n)
     d = _dev()
@@ -214,11 +206,11 @@ def test_distmult_pose_sized_and_pair(n, decoder_path):
         assert rel_err(pos, pos_ref) < TOL and rel_err(neg, neg_ref) < TOL
         assert rel_err(zc.grad, zr.grad) < TOL and rel_err(wc.grad, wr.grad) < TOL
         res.append((pos.detach(), neg.detach(), zc.grad.clone(), wc.grad.clone()))
-    for a, b in zip(*res):                       # same kernels, same summation order
-        assert torch.equal(a, b)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert rel_err(res[1][2], res[0][2]) < 1e-6 and rel_err(res[1][3], res[0][3]) < 1e-6
 
 
-def test_distmult_backward_deterministic_and_hub_rows(decoder_path):
+def test_distmult_backward_deterministic_and_hub_rows():
     from gripnet_b200 import ops
     rs = np.random.RandomState(3)
     d = _dev()
@@ -301,37 +293,65 @@ def test_losses_and_elementwise():
     assert torch.equal(r, torch.where(y > 0, a, torch.zeros_like(a)))
 
 
-@pytest.mark.parametrize("n,D,r,e", [(40, 20, 3, 900), (645, 80, 16, 400_000), (7, 8, 2, 300)])
-def test_distmult_dense_pair_matches_float64_and_the_gather_path(n, D, r, e, monkeypatch):
-    """Dense-relation decoder (csrc/decoder_dense.cu, GRIPNET_B200_DECODER=dense; not the default path): same
-    scores and gradients as the float64 evaluation and as the gather-multiply-reduce kernels."""
+def test_distmult_pair_edge_cases():
+    """Same tensor as positive AND negative list (one shared structure: the two walks must not race), an
+    in-place rewrite of the indices between forward and backward (must raise, not mis-pair), out-of-range
+    ids (IndexError like the reference's indexing), empty edge lists."""
     from gripnet_b200 import ops
-    from gripnet_b200.decoder import multiRelaInnerProductDecoder
-    rs = np.random.RandomState(n)
+    rs = np.random.RandomState(9)
     d = _dev()
+    n, D, r, e = 50, 80, 4, 20_000
     z = torch.randn(n, D, dtype=torch.float64) * 0.3
     w = torch.randn(r, D, dtype=torch.float64)
-    ei = torch.from_numpy(rs.randint(0, n, (2, e)))          # duplicates and self-loops included
-    ni = torch.from_numpy(rs.randint(0, n, (2, e)))
+    ei = torch.from_numpy(rs.randint(0, n, (2, e)))
     et = torch.from_numpy(np.sort(rs.randint(0, r, e)))
     zr, wr = z.clone().requires_grad_(True), w.clone().requires_grad_(True)
-    pos_ref = torch.sigmoid((zr[ei[0]] * zr[ei[1]] * wr[et]).sum(1))
-    neg_ref = torch.sigmoid((zr[ni[0]] * zr[ni[1]] * wr[et]).sum(1))
-    gp = torch.linspace(-1, 1, e, dtype=torch.float64)
-    gn = torch.linspace(0.5, -0.5, e, dtype=torch.float64)
-    ((pos_ref * gp).sum() + (neg_ref * gn).sum()).backward()
-    dec = multiRelaInnerProductDecoder(D, r).to(d)
-    res = []
-    for path in ("dense", "global"):
-        monkeypatch.setattr(ops, "DECODER_PATH", path)
-        with torch.no_grad():
-            dec.weight.copy_(w.float())
-        dec.weight.grad = None
-        zc = z.float().to(d).requires_grad_(True)
-        pos, neg = dec.score_pair(zc, ei.to(d), ni.to(d), et.to(d))
-        ((pos * gp.float().to(d)).sum() + (neg * gn.float().to(d)).sum()).backward()
-        assert rel_err(pos, pos_ref) < TOL and rel_err(neg, neg_ref) < TOL, path
-        assert rel_err(zc.grad, zr.grad) < TOL and rel_err(dec.weight.grad, wr.grad) < TOL, path
-        res.append((pos.detach().clone(), zc.grad.clone()))
-    again = dec.score_pair(z.float().to(d), ei.to(d), ni.to(d), et.to(d))[0]     # "global" again: deterministic
-    assert torch.equal(again, res[1][0])
+    ref = torch.sigmoid((zr[ei[0]] * zr[ei[1]] * wr[et]).sum(1))
+    (ref.sum() * 2).backward()
+    zc, wc = z.float().to(d).requires_grad_(True), w.float().to(d).requires_grad_(True)
+    eid, etd = ei.to(d), et.to(d)
+    pos, neg = ops.DistMultPair.apply(zc, wc, eid, eid, etd, True)
+    (pos.sum() + neg.sum()).backward()
+    assert torch.equal(pos, neg) and rel_err(pos, ref) < TOL
+    assert rel_err(zc.grad, zr.grad) < TOL and rel_err(wc.grad, wr.grad) < TOL
+    # in-place rewrite between forward and backward
+    zc2 = z.float().to(d).requires_grad_(True)
+    buf = eid.clone()
+    out = ops.DistMult.apply(zc2, wc.detach(), buf, etd, True)
+    buf.copy_(eid.flip(1))
+    with pytest.raises(RuntimeError, match="modified in place"):
+        out.sum().backward()
+    # out-of-range ids
+    bad = eid.clone()
+    bad[0, 5] = n
+    with pytest.raises(IndexError):
+        ops.DistMult.apply(zc.detach(), wc.detach(), bad, etd, True)
+    bad_t = etd.clone()
+    bad_t[-1] = r
+    with pytest.raises(IndexError):
+        ops.DistMult.apply(zc.detach(), wc.detach(), eid, bad_t, True)
+    with pytest.raises(IndexError):
+        ops.MultiClass.apply(zc.detach(), torch.randn(D, 3, device=d), torch.tensor([0, n], device=d), True)
+    with pytest.raises(IndexError):
+        ops.NodeClassLoss.apply(torch.rand(4, 3, device=d), torch.tensor([0, 1, 2, 3], device=d))
+    # empty lists
+    z0 = z.float().to(d).requires_grad_(True)
+    empty = torch.zeros((2, 0), dtype=torch.int64, device=d)
+    o = ops.DistMult.apply(z0, wc.detach().requires_grad_(True), empty, torch.zeros(0, dtype=torch.int64, device=d), True)
+    assert o.numel() == 0
+    o.sum().backward()
+    assert float(z0.grad.abs().sum()) == 0.0
+
+
+def test_mean3_matches_the_reference_expression():
+    """(z + z1 + emb) / 3 of GripNet-freebase-d.py:160-161: bit-identical forward (same association order, true
+    division), gradient g / 3 on all three inputs."""
+    from gripnet_b200 import ops
+    d = _dev()
+    a, b, c = (torch.randn(1000, 128, device=d, requires_grad=True) for _ in range(3))
+    out = ops.mean3(a, b, c)
+    assert torch.equal(out, (a + b + c) / 3)
+    g = torch.randn_like(out)
+    out.backward(g)
+    for t in (a, b, c):
+        assert rel_err(t.grad, (g / 3)) < 1e-6

@@ -282,3 +282,32 @@ def test_cuda_graph_capture_of_a_full_step():
     for k, v in m.named_parameters():
         if v.grad is not None:
             assert torch.equal(v.grad, eager[k]), k
+
+
+def test_encoder_rgcn_forward_backward_matches_the_port():
+    """``gripnet.encoder.RGCN`` (reference ``encoder.py:6-25``; its ``forward`` reads a misnamed attribute there,
+    so the check is against what it evidently computes: project by the embedding, then two myRGCN layers with
+    no activation in between) and ``ops.MatMul`` — forward and every gradient against the CPU port."""
+    import gripnet_b200 as gb
+    from oracle import port, synth
+    d = torch.device("cuda:0")
+    g = synth.pose_small()
+    n, r = g["n_d"], g["n_rel"]
+    torch.manual_seed(5)
+    enc = gb.encoder.RGCN(24, 16, 12, 8, r, 4).to(d)
+    x = torch.randn(n, 24)
+    xc = x.to(d).requires_grad_(True)
+    ei, et, rl = g["dd_edge_index"].to(d), g["dd_edge_type"].to(d), g["dd_range_list"]
+    out = enc(xc, ei, et, rl)
+    gvec = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * gvec.to(d)).sum().backward()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc.named_parameters()}
+    xr = x.clone().requires_grad_(True)
+    h = xr @ p["embedding"]
+    h = port.rgcn_conv(h, p["rgcn1.basis"], p["rgcn1.att"], p["rgcn1.root"], None, g["dd_edge_index"], rl)
+    ref = port.rgcn_conv(h, p["rgcn2.basis"], p["rgcn2.att"], p["rgcn2.root"], None, g["dd_edge_index"], rl)
+    (ref * gvec).sum().backward()
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(xc.grad, xr.grad) < 1e-5
+    for k, v in enc.named_parameters():
+        assert rel_err(v.grad, p[k].grad) < 1e-5, k

@@ -188,7 +188,7 @@ def test_edge_and_index_prep(n, r, e):
     assert int(st.csr.row_counter.abs().sum()) == 0 and int(es.node.row_counter.abs().sum()) == 0
 
 
-@pytest.mark.parametrize("n_rows", [400, 3000, 20000])       # one-block builder (<= 8192 rows) and the scan path
+@pytest.mark.parametrize("n_rows", [400, 3000, 20000, 50000])   # one-block builder (<= 32768 rows) and the scan path
 @pytest.mark.parametrize("chunk_len", [32, 64, 1024])
 def test_chunk_list_covers_every_entry_once(chunk_len, n_rows):
     from gripnet_b200.graph import Csr
@@ -209,3 +209,76 @@ def test_chunk_list_covers_every_entry_once(chunk_len, n_rows):
         end = min(cbeg[c] + chunk_len, rowptr[crow[c] + 1])
         seen[cbeg[c]:end] += 1
     assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("case", ["square", "square_weighted_improved", "bipartite", "bipartite_weighted"])
+def test_partitioned_prep_equals_slices_of_the_global_csr(case, world):
+    """Per-rank graph prep of the destination-partitioned path (gn_edge_filter + gn_gcn_part_structure +
+    gn_gcn_part_values): every rank's rows, built ONLY from the edges that touch its block plus the all-gathered
+    deg^-1/2 vector, are BIT-IDENTICAL to the matching rows of the single-GPU CSR pair (columns, coefficients,
+    degrees) — self-loops, duplicate edges, empty rows and an uneven last block included."""
+    from gripnet_b200.graph import GcnGraph, filter_edges, part_structure, part_values
+    from gripnet_b200.parallel import block_bounds, block_size
+    rs = np.random.RandomState(world)
+    d = _dev()
+    bip = case.startswith("bipartite")
+    n_src, n_dst = (1003, 157) if bip else (1003, 1003)
+    e = 20_000
+    ei = np.stack([rs.randint(0, n_src, e), rs.randint(0, n_dst, e)])
+    if not bip:
+        ei[1, :300] = ei[0, :300]                 # self-loops (some nodes several times)
+        ei[:, 300:600] = ei[:, 600:900]           # duplicate edges
+    ei[1, ei[1] == 5] = 6                          # an empty target row
+    w = rs.uniform(0.5, 1.5, e).astype(np.float32) if "weighted" in case else None
+    improved = "improved" in case
+    ei_t = torch.from_numpy(ei).to(d)
+    w_t = None if w is None else torch.from_numpy(w).to(d)
+    g = GcnGraph(ei_t, n_src, n_dst, w_t, improved, bipartite=bip)
+    fill, loops = (2.0 if improved else 1.0), (0 if bip else 1)
+    b_dst = block_size(n_dst, world)
+    parts, dis_all = [], torch.zeros(world * b_dst, device=d)
+    for r in range(world):
+        d0, d1 = block_bounds(n_dst, world, r)
+        shard, ws = filter_edges(ei_t, w_t, False, d0, d1)
+        keep = (ei[1] >= d0) & (ei[1] < d1)
+        assert np.array_equal(shard.cpu().numpy(), ei[:, keep])            # order-preserving filter
+        rowptr, col, val, deg, dis, nnz = part_structure(shard.contiguous(), ws, 1, d0, d1 - d0, loops, fill, True)
+        dis_all[r * b_dst: r * b_dst + (d1 - d0)] = dis[: d1 - d0]
+        parts.append((d0, d1, rowptr, col, val, deg, nnz))
+    g_rp, g_col, g_val = g.fwd.rowptr.cpu().numpy(), g.fwd.col.cpu().numpy(), g.fwd.val.cpu().numpy()
+    for d0, d1, rowptr, col, val, deg, nnz in parts:
+        part_values(rowptr, col, val, d1 - d0, d0, None if bip else dis_all, dis_all, False)
+        a, b = g_rp[d0], g_rp[d1]
+        assert nnz == b - a
+        assert np.array_equal(rowptr[: d1 - d0 + 1].cpu().numpy(), g_rp[d0:d1 + 1] - a)
+        assert np.array_equal(col[:nnz].cpu().numpy(), g_col[a:b])
+        assert np.array_equal(val[:nnz].cpu().numpy(), g_val[a:b])         # bit-identical fp32 coefficients
+        assert np.array_equal(deg[: d1 - d0].cpu().numpy(), g.deg[d0:d1].cpu().numpy())
+    t_rp, t_col, t_val = g.bwd.rowptr.cpu().numpy(), g.bwd.col.cpu().numpy(), g.bwd.val.cpu().numpy()
+    for r in range(world):
+        s0, s1 = block_bounds(n_src, world, r)
+        shard, ws = filter_edges(ei_t, w_t, True, s0, s1)
+        rowptr, col, val, _, _, nnz = part_structure(shard.contiguous(), ws, 0, s0, s1 - s0, loops, fill, False)
+        part_values(rowptr, col, val, s1 - s0, s0, None if bip else dis_all, dis_all, True)
+        a, b = t_rp[s0], t_rp[s1]
+        assert nnz == b - a
+        assert np.array_equal(rowptr[: s1 - s0 + 1].cpu().numpy(), t_rp[s0:s1 + 1] - a)
+        assert np.array_equal(col[:nnz].cpu().numpy(), t_col[a:b])
+        assert np.array_equal(val[:nnz].cpu().numpy(), t_val[a:b])
+
+
+@pytest.mark.parametrize("n,r,e", [(120, 7, 4000), (645, 16, 50000), (1500, 300, 20000), (5, 1, 0)])
+def test_pair_prep(n, r, e):
+    """(node, relation) pair CSR of the one-pass decoder backward: bit-exact vs a stable argsort of
+    node * n_rel + rel over the 2E endpoint entries."""
+    from gripnet_b200.graph import PairStruct
+    rs = np.random.RandomState(11)
+    ei = rs.randint(0, n, size=(2, e))
+    et = rs.randint(0, r, size=e)
+    ps = PairStruct(torch.from_numpy(ei).to(_dev()), torch.from_numpy(et).to(_dev()), n, r, exact=True)
+    keys = np.concatenate([ei[0], ei[1]]) * r + np.concatenate([et, et])
+    rp, perm = port.csr_from_edges(keys, n * r)
+    assert np.array_equal(ps.csr.rowptr.cpu().numpy(), rp)
+    assert np.array_equal(ps.ent_other[: 2 * e].cpu().numpy(), np.concatenate([ei[1], ei[0]])[perm])
+    assert np.array_equal(ps.ent_eid[: 2 * e].cpu().numpy(), np.where(perm < e, perm, perm - e))

@@ -142,3 +142,23 @@ def test_utils_negative_sampling_on_cuda_tensors():
     t = u.typed_negative_sampling(pos, 300, rl)
     for s, e in rl.tolist():
         assert not np.isin((t[0, s:e] * 300 + t[1, s:e]).cpu().numpy(), code_p[s:e]).any()
+
+
+@pytest.mark.gpu
+def test_utils_negative_sampling_cache_misses_do_not_repeat_a_stream():
+    """A fresh clone / slice of the positives on every call misses the sampler cache: each miss must still
+    draw from its own stream (the reference draws fresh numpy randoms per call, utils.py:104-110), and more
+    live edge tensors than the cache holds must keep working (LRU eviction)."""
+    import gripnet_b200.utils as u
+    d = torch.device("cuda:0")
+    rs = np.random.RandomState(1)
+    pos = torch.from_numpy(rs.randint(0, 300, (2, 4000))).to(d)
+    draws = [u.negative_sampling(pos.clone(), 300) for _ in range(4)]
+    for i in range(4):
+        for j in range(i):
+            assert not torch.equal(draws[i], draws[j])
+    slices = [pos[:, i * 50:(i + 1) * 50].contiguous() for i in range(u._SAMPLER_CAPACITY + 6)]
+    first = [u.negative_sampling(s, 300) for s in slices]
+    again = [u.negative_sampling(s, 300) for s in slices]
+    assert len(u._samplers) <= u._SAMPLER_CAPACITY
+    assert sum(torch.equal(a, b) for a, b in zip(first, again)) == 0
