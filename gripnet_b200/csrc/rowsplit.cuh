@@ -148,8 +148,10 @@ __device__ __forceinline__ void sum_partials(const float* __restrict__ rows, int
 // Finish a row.  `acc[NV]` holds this warp's slot-reduced sums (valid on slot 0);
 // `width` = number of floats per row; feature lane `fl` owns floats
 // [ (v*LPE + fl)*VEC , +VEC ) for v < NV.  `emit(v, f, vec)` writes the result.
+// Returns true (warp-uniform) on the warp that emitted the row: the only chunk of the row, or the last of its
+// chunks to arrive.
 template <int LPE, int VEC, int NV, int TAIL_DEPTH = 1, typename Emit>
-__device__ __forceinline__ void finish_row(const gn_csr& csr, const ChunkInfo& ci, Vec<VEC> (&acc)[NV], int width,
+__device__ __forceinline__ bool finish_row(const gn_csr& csr, const ChunkInfo& ci, Vec<VEC> (&acc)[NV], int width,
                                            float* __restrict__ partial, Emit emit) {
   constexpr int EPI = 32 / LPE;
   const int lane = threadIdx.x & 31;
@@ -162,7 +164,7 @@ __device__ __forceinline__ void finish_row(const gn_csr& csr, const ChunkInfo& c
         if (f < width) emit(v, f, acc[v]);
       }
     }
-    return;
+    return true;
   }
   // Partial-sum slots: a row with k > 1 chunks owns slots [2*(first_chunk-row), +k).
   // first_chunk-row = number of EXTRA chunks in earlier rows and k <= 2*(k-1), so the
@@ -180,7 +182,7 @@ __device__ __forceinline__ void finish_row(const gn_csr& csr, const ChunkInfo& c
   int last = 0;
   if (lane == 0) last = (atomicAdd(csr.row_counter + ci.row, 1) == ci.n_chunks_of_row - 1) ? 1 : 0;
   last = __shfl_sync(kFull, last, 0);
-  if (!last) return;
+  if (!last) return false;
   __threadfence();
   Vec<VEC> s[NV];
   sum_partials<LPE, VEC, NV, TAIL_DEPTH>(partial + pbase * width, ci.n_chunks_of_row, width, slot, fl, s);
@@ -191,6 +193,7 @@ __device__ __forceinline__ void finish_row(const gn_csr& csr, const ChunkInfo& c
     if (slot == 0 && f < width) emit(v, f, s[v]);
   }
   if (lane == 0) csr.row_counter[ci.row] = 0;  // every warp of this row has arrived: safe to re-arm
+  return true;
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -194,6 +194,23 @@ int gn_spmm(const gn_csr* csr, const float* x, int64_t ldx, int32_t F,
             const float* row_scale, const float* bias, const float* addend, int64_t ld_addend,
             int relu, float* out, int64_t ldo, float* partial, void* stream);
 
+/* gn_spmm with a fused ROW TRANSFORM in its epilogue: while the finished output row h = out[i, 0:F] is still in
+ * registers the warp also writes
+ *   y2[i, 0:n2] = h . op(W) (+ addend2[i]) (zeroed where relu_mask2[i] <= 0),
+ *   op(W)[k][j] = W[k*ldw + j] (transW == 0)  or  W[j*ldw + k] (transW != 0).
+ * Forward: the NEXT layer's dense transform Y_{l+1} = H_l W_{l+1} (gripnet/layers.py:73 of the next conv);
+ * backward: the previous layer's gradient dH_{l-1} = dY_l W_l^T + concat-slice gradient, ReLU-masked
+ * (autograd of layers.py:73 and :279).  Removes one GEMM launch per layer from the step's dependency chain and an
+ * [N, F] round trip; available when gn_spmm_fused_ok(F, n2) (F % 4 == 0, F <= 128, n2 <= 64, F*n2 <= 1024:
+ * the narrow layers of the pose family) and the 128-bit alignment rules of gn_spmm hold. */
+int gn_spmm_fused_ok(int32_t F, int32_t n2);
+int gn_spmm_fused(const gn_csr* csr, const float* x, int64_t ldx, int32_t F,
+                  const float* row_scale, const float* bias, const float* addend, int64_t ld_addend,
+                  int relu, float* out, int64_t ldo, float* partial,
+                  const float* W, int32_t n2, int64_t ldw, int transW, float* y2, int64_t ldy2,
+                  const float* addend2, int64_t ld_addend2, const float* relu_mask2, int64_t ld_mask2,
+                  void* stream);
+
 /* ---- K2/K6: dense transforms (fp32 FFMA, CUDA cores)  --------------------- */
 /* C[b] = epilogue( alpha * op(A[b]) * op(B[b]) ), b in [0,batch):
  *   op(A) is M x K (transA: stored K x M), op(B) is K x N (transB: stored N x K);
