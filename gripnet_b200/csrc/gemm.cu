@@ -304,3 +304,131 @@ extern "C" int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
   }
   return GN_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Tall-skinny TN product for the weight gradients of the narrow layers:  C[K, F] = A^T B,  A: [n, K],
+// B: [n, F], K * F <= kTnMaxOut, n = number of nodes (the reduction).  dW = H_{l-1}^T dY of
+// gripnet/layers.py:73 under autograd.  ONE launch: every CTA reduces its slab of rows into a private
+// [K, F] partial (operands staged through shared memory with 128-bit loads), the partials go to `ws`, and the
+// LAST CTA to arrive (integer arrival counter) adds them in CTA order — a fixed summation order, so the
+// result is bit-reproducible — instead of the generic split-K kernel plus its separate reduce launch
+// (18-21 us + 25 us at pose-0 size, at the tail of the backward pass).
+// ---------------------------------------------------------------------------------------------------
+namespace gn {
+
+constexpr int kTnMaxOut = 2048;        // outputs per product: <= 8 accumulators per thread
+constexpr int kTnRows = 32;            // rows per staged tile
+constexpr int kTnMaxAcc = kTnMaxOut / 256;
+
+__global__ void __launch_bounds__(256) tn_gemm_kernel(const float* __restrict__ A, int64_t lda,
+                                                      const float* __restrict__ B, int64_t ldb, int64_t n, int K, int F,
+                                                      int rows_per_cta, float* __restrict__ C, int64_t ldc,
+                                                      float* __restrict__ partial, unsigned int* __restrict__ counter) {
+  extern __shared__ float tn_smem[];
+  float* As = tn_smem;                    // [kTnRows][K]
+  float* Bs = tn_smem + kTnRows * K;      // [kTnRows][F]
+  __shared__ int s_last;
+  const int n_out = K * F;
+  const int64_t r0 = int64_t(blockIdx.x) * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
+  float acc[kTnMaxAcc];
+#pragma unroll
+  for (int i = 0; i < kTnMaxAcc; ++i) acc[i] = 0.f;
+  const bool vec = (K % 4 == 0) && (F % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+  for (int64_t t0 = r0; t0 < r1; t0 += kTnRows) {
+    const int rows = int(r1 - t0 < kTnRows ? r1 - t0 : kTnRows);
+    if (vec) {
+      const int k4 = K / 4, f4 = F / 4;
+      for (int i = threadIdx.x; i < rows * k4; i += 256) {
+        const int r = i / k4, c = i - r * k4;
+        *reinterpret_cast<float4*>(As + r * K + 4 * c) = ldg4(A + (t0 + r) * lda + 4 * c);
+      }
+      for (int i = threadIdx.x; i < rows * f4; i += 256) {
+        const int r = i / f4, c = i - r * f4;
+        *reinterpret_cast<float4*>(Bs + r * F + 4 * c) = ldg4(B + (t0 + r) * ldb + 4 * c);
+      }
+    } else {
+      for (int i = threadIdx.x; i < rows * K; i += 256) As[i] = __ldg(A + (t0 + i / K) * lda + i % K);
+      for (int i = threadIdx.x; i < rows * F; i += 256) Bs[i] = __ldg(B + (t0 + i / F) * ldb + i % F);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kTnMaxAcc; ++i) {
+      const int o = int(threadIdx.x) + 256 * i;
+      if (o < n_out) {
+        const int k = o / F, f = o - k * F;
+        float a = acc[i];
+        for (int r = 0; r < rows; ++r) a = fmaf(As[r * K + k], Bs[r * F + f], a);
+        acc[i] = a;
+      }
+    }
+    __syncthreads();
+  }
+  float* mine = partial + int64_t(blockIdx.x) * n_out;
+#pragma unroll
+  for (int i = 0; i < kTnMaxAcc; ++i) {
+    const int o = int(threadIdx.x) + 256 * i;
+    if (o < n_out) mine[o] = acc[i];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int G = gridDim.x;
+#pragma unroll
+  for (int i = 0; i < kTnMaxAcc; ++i) {
+    const int o = int(threadIdx.x) + 256 * i;
+    if (o < n_out) {
+      float s = 0.f;
+      int g = 0;
+      for (; g + 3 < G; g += 4) {            // loads issued together, adds kept in CTA order
+        const float a = __ldcg(partial + int64_t(g) * n_out + o), b = __ldcg(partial + int64_t(g + 1) * n_out + o);
+        const float c = __ldcg(partial + int64_t(g + 2) * n_out + o), d = __ldcg(partial + int64_t(g + 3) * n_out + o);
+        s += a; s += b; s += c; s += d;
+      }
+      for (; g < G; ++g) s += __ldcg(partial + int64_t(g) * n_out + o);
+      C[int64_t(o / F) * ldc + (o % F)] = s;
+    }
+  }
+  if (threadIdx.x == 0) *counter = 0;
+}
+
+static int tn_ctas(int64_t n) {
+  int64_t g = ceil_div(n, 64);
+  if (g > 148) g = 148;
+  return int(g < 1 ? 1 : g);
+}
+
+}  // namespace gn
+
+extern "C" int gn_tn_gemm_ok(int32_t K, int32_t F) {
+  return (K > 0 && F > 0 && int64_t(K) * F <= gn::kTnMaxOut && (K + F) * gn::kTnRows * 4 <= 48 * 1024) ? 1 : 0;
+}
+
+extern "C" size_t gn_tn_gemm_workspace_bytes(int64_t n, int32_t K, int32_t F) {
+  return 256 + size_t(gn::tn_ctas(n)) * size_t(K) * size_t(F) * 4;
+}
+
+extern "C" int gn_tn_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t K, int32_t F,
+                          float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
+  if (n < 0 || !gn_tn_gemm_ok(K, F) || !C) return GN_ERR_ARG;
+  cudaStream_t st = gn::as_stream(stream);
+  if (n == 0) {
+    if (cudaMemset2DAsync(C, size_t(ldc) * 4, 0, size_t(F) * 4, size_t(K), st) != cudaSuccess) return GN_ERR_CUDA;
+    return GN_OK;
+  }
+  if (!A || !B) return GN_ERR_ARG;
+  if (!ws || ws_bytes < gn_tn_gemm_workspace_bytes(n, K, F) || (reinterpret_cast<uintptr_t>(ws) & 15)) return GN_ERR_WORKSPACE;
+  const int G = gn::tn_ctas(n);
+  const int rows_per_cta = int(gn::ceil_div(n, G));
+  unsigned int* counter = static_cast<unsigned int*>(ws);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + 256);
+  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return GN_ERR_CUDA;
+  const size_t smem = size_t(K + F) * gn::kTnRows * sizeof(float);
+  GN_LAUNCH(gn::tn_gemm_kernel, (unsigned)G, 256, smem, st, A, lda, B, ldb, n, K, F, rows_per_cta, C, ldc, partial,
+            counter);
+  return GN_OK;
+}

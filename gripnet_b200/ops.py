@@ -180,6 +180,19 @@ def rel_transform(x, w, y, r, k, f, device):
     sgemm(False, False, n, f, k, x.ptr, x.ld, w.data_ptr(), f, y.ptr, y.ld, device, batch=r, sa=0, sb=k * f, sc=f)
 
 
+def weight_grad(a, b, out, device):
+    """``out[K, F] = a^T b`` (``a``: M [n, K], ``b``: M [n, F]; the reduction runs over the nodes): the one-launch
+    tall-skinny kernel for the narrow layers, the generic split-K GEMM otherwise."""
+    lib = _lib.load()
+    k, f, n = a.f, b.f, a.n
+    if lib.gn_tn_gemm_ok(k, f):
+        ws = _ws(lib.gn_tn_gemm_workspace_bytes(n, k, f), device)
+        _lib.check(lib.gn_tn_gemm(a.ptr, a.ld, b.ptr, b.ld, n, k, f, out.data_ptr(), f, _ptr(ws), ws.numel(),
+                                  _stream()), "gn_tn_gemm")
+        return
+    sgemm(True, False, k, f, n, a.ptr, a.ld, b.ptr, b.ld, out.data_ptr(), f, device)
+
+
 def map2d(op, src, dst):
     _lib.check(_lib.load().gn_map2d(op, src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.f, _stream()), "gn_map2d")
 
@@ -332,8 +345,7 @@ class GcnStack(torch.autograd.Function):
                 dw = torch.empty((k, f), dtype=torch.float32, device=dev)
                 # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
                 with br(dy.t, h_prev.t):
-                    sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f,
-                          dev)
+                    weight_grad(h_prev, dy, dw, dev)
                 grads[2 * (l - 1)] = _reduce(dctx, dw)
             dz_slot = None
             if need_prev:
@@ -479,7 +491,7 @@ class RgcnStack(torch.autograd.Function):
             if ctx.needs_input_grad[base + 2]:
                 droot = torch.empty((k, f), dtype=torch.float32, device=dev)
                 with br(dz.t, h_prev.t):
-                    sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev)
+                    weight_grad(h_prev, dz, droot, dev)
                 grads[4 * (l - 1) + 2] = _reduce(dctx, droot)
             if ctx.needs_input_grad[base] or ctx.needs_input_grad[base + 1]:
                 # dW[r] = H_{l-1}^T dY[:, r, :]

@@ -231,6 +231,15 @@ int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
              const float* relu_mask, int64_t ld_mask, const int64_t* a_rows,
              int32_t split_k, float* ws, size_t ws_bytes, void* stream);
 
+/* Tall-skinny TN product for the weight gradients of the narrow layers: C[K, F] = A^T B with A [n, K], B [n, F],
+ * n = number of nodes (dW = H_{l-1}^T dY, autograd of gripnet/layers.py:73).  One launch: per-CTA partial
+ * products over row slabs, summed in CTA order by the last CTA to arrive (deterministic).  Available when
+ * gn_tn_gemm_ok(K, F) (K * F <= 2048); `ws` holds gn_tn_gemm_workspace_bytes(n, K, F) bytes, 16-byte aligned. */
+int gn_tn_gemm_ok(int32_t K, int32_t F);
+size_t gn_tn_gemm_workspace_bytes(int64_t n, int32_t K, int32_t F);
+int gn_tn_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t K, int32_t F,
+               float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K2/K6 tensor path: tcgen05 (kind::tf32) with 3xTF32 error compensation -- */
 /* C = epilogue( A[M,K] * op(B) ),  op(B) = B [K,N] (transB == 0) or B^T with B stored [N,K].
  * Each operand element is split hi + lo in TF32 while it is staged and three MMAs per k-step
