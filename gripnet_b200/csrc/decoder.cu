@@ -280,12 +280,24 @@ __global__ void __launch_bounds__(kGradThreads) distmult_grads_kernel(const floa
     const int f = D <= kGradThreads ? int(threadIdx.x) % D : f0 + int(threadIdx.x);
     float acc = 0.f;
     if (g < G && f < D) {
-      for (int i = g; i < n_terms; i += G) {
-        const int64_t t = is_dz ? (int64_t(row) * n_rel + i) * D + f : (int64_t(i) * n_rel + row) * D + f;
-        float tv = __ldg(T + t);
-        if (T2) tv += __ldg(T2 + t);
-        const float o = is_dz ? __ldg(w + int64_t(i) * D + f) : __ldg(z + int64_t(i) * ldz + f);
-        acc = fmaf(tv, o, acc);
+      // kU terms per round: every load of the round is issued before the first add (the terms are L2 / HBM
+      // round trips), the adds stay in term order
+      constexpr int kU = 6;
+      for (int i0 = g; i0 < n_terms; i0 += kU * G) {
+        float tv[kU], ov[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int i = i0 + u * G;
+          tv[u] = ov[u] = 0.f;
+          if (i < n_terms) {
+            const int64_t t = is_dz ? (int64_t(row) * n_rel + i) * D + f : (int64_t(i) * n_rel + row) * D + f;
+            tv[u] = __ldg(T + t);
+            if (T2) tv[u] += __ldg(T2 + t);
+            ov[u] = is_dz ? __ldg(w + int64_t(i) * D + f) : __ldg(z + int64_t(i) * ldz + f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) acc = fmaf(tv[u], ov[u], acc);
       }
       red[g * D + (f - f0)] = acc;
     }

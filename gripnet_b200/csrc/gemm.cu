@@ -319,6 +319,7 @@ namespace gn {
 constexpr int kTnMaxOut = 2048;        // outputs per product: <= 8 accumulators per thread
 constexpr int kTnRows = 32;            // rows per staged tile
 constexpr int kTnMaxAcc = kTnMaxOut / 256;
+constexpr int kTnMaxCtas = 32;         // few partials: the last CTA's ordered sum stays a handful of round trips
 
 __global__ void __launch_bounds__(256) tn_gemm_kernel(const float* __restrict__ A, int64_t lda,
                                                       const float* __restrict__ B, int64_t ldb, int64_t n, int K, int F,
@@ -331,46 +332,59 @@ __global__ void __launch_bounds__(256) tn_gemm_kernel(const float* __restrict__ 
   const int n_out = K * F;
   const int64_t r0 = int64_t(blockIdx.x) * rows_per_cta;
   const int64_t r1 = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
-  float acc[kTnMaxAcc];
+  // two accumulators per output (even / odd rows of a tile) halve the dependent FMA chain; they are added
+  // in a fixed order, so the result does not depend on timing
+  float acc0[kTnMaxAcc], acc1[kTnMaxAcc];
+  int ok[kTnMaxAcc], of[kTnMaxAcc];
 #pragma unroll
-  for (int i = 0; i < kTnMaxAcc; ++i) acc[i] = 0.f;
+  for (int i = 0; i < kTnMaxAcc; ++i) {
+    acc0[i] = acc1[i] = 0.f;
+    const int o = int(threadIdx.x) + 256 * i;
+    ok[i] = o < n_out ? o / F : -1;
+    of[i] = o < n_out ? o - (o / F) * F : 0;
+  }
   const bool vec = (K % 4 == 0) && (F % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
   for (int64_t t0 = r0; t0 < r1; t0 += kTnRows) {
     const int rows = int(r1 - t0 < kTnRows ? r1 - t0 : kTnRows);
     if (vec) {
       const int k4 = K / 4, f4 = F / 4;
-      for (int i = threadIdx.x; i < rows * k4; i += 256) {
+      for (int i = threadIdx.x; i < kTnRows * k4; i += 256) {
         const int r = i / k4, c = i - r * k4;
-        *reinterpret_cast<float4*>(As + r * K + 4 * c) = ldg4(A + (t0 + r) * lda + 4 * c);
+        *reinterpret_cast<float4*>(As + r * K + 4 * c) =
+            r < rows ? ldg4(A + (t0 + r) * lda + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (int i = threadIdx.x; i < rows * f4; i += 256) {
+      for (int i = threadIdx.x; i < kTnRows * f4; i += 256) {
         const int r = i / f4, c = i - r * f4;
-        *reinterpret_cast<float4*>(Bs + r * F + 4 * c) = ldg4(B + (t0 + r) * ldb + 4 * c);
+        *reinterpret_cast<float4*>(Bs + r * F + 4 * c) =
+            r < rows ? ldg4(B + (t0 + r) * ldb + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
-      for (int i = threadIdx.x; i < rows * K; i += 256) As[i] = __ldg(A + (t0 + i / K) * lda + i % K);
-      for (int i = threadIdx.x; i < rows * F; i += 256) Bs[i] = __ldg(B + (t0 + i / F) * ldb + i % F);
+      for (int i = threadIdx.x; i < kTnRows * K; i += 256) As[i] = i / K < rows ? __ldg(A + (t0 + i / K) * lda + i % K) : 0.f;
+      for (int i = threadIdx.x; i < kTnRows * F; i += 256) Bs[i] = i / F < rows ? __ldg(B + (t0 + i / F) * ldb + i % F) : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kTnMaxAcc; ++i) {
-      const int o = int(threadIdx.x) + 256 * i;
-      if (o < n_out) {
-        const int k = o / F, f = o - k * F;
-        float a = acc[i];
-        for (int r = 0; r < rows; ++r) a = fmaf(As[r * K + k], Bs[r * F + f], a);
-        acc[i] = a;
+      if (ok[i] >= 0) {
+        const float* ap = As + ok[i];
+        const float* bp = Bs + of[i];
+        float a0 = acc0[i], a1 = acc1[i];
+#pragma unroll 8
+        for (int r = 0; r < kTnRows; r += 2) {     // rows past the slab are zero-filled
+          a0 = fmaf(ap[r * K], bp[r * F], a0);
+          a1 = fmaf(ap[(r + 1) * K], bp[(r + 1) * F], a1);
+        }
+        acc0[i] = a0;
+        acc1[i] = a1;
       }
     }
     __syncthreads();
   }
   float* mine = partial + int64_t(blockIdx.x) * n_out;
 #pragma unroll
-  for (int i = 0; i < kTnMaxAcc; ++i) {
-    const int o = int(threadIdx.x) + 256 * i;
-    if (o < n_out) mine[o] = acc[i];
-  }
+  for (int i = 0; i < kTnMaxAcc; ++i)
+    if (ok[i] >= 0) mine[int(threadIdx.x) + 256 * i] = acc0[i] + acc1[i];
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
@@ -380,25 +394,23 @@ __global__ void __launch_bounds__(256) tn_gemm_kernel(const float* __restrict__ 
   const int G = gridDim.x;
 #pragma unroll
   for (int i = 0; i < kTnMaxAcc; ++i) {
-    const int o = int(threadIdx.x) + 256 * i;
-    if (o < n_out) {
+    if (ok[i] >= 0) {
+      const int o = int(threadIdx.x) + 256 * i;
+      float v[kTnMaxCtas];
+#pragma unroll
+      for (int g = 0; g < kTnMaxCtas; ++g) v[g] = g < G ? __ldcg(partial + int64_t(g) * n_out + o) : 0.f;   // all in flight
       float s = 0.f;
-      int g = 0;
-      for (; g + 3 < G; g += 4) {            // loads issued together, adds kept in CTA order
-        const float a = __ldcg(partial + int64_t(g) * n_out + o), b = __ldcg(partial + int64_t(g + 1) * n_out + o);
-        const float c = __ldcg(partial + int64_t(g + 2) * n_out + o), d = __ldcg(partial + int64_t(g + 3) * n_out + o);
-        s += a; s += b; s += c; s += d;
-      }
-      for (; g < G; ++g) s += __ldcg(partial + int64_t(g) * n_out + o);
-      C[int64_t(o / F) * ldc + (o % F)] = s;
+#pragma unroll
+      for (int g = 0; g < kTnMaxCtas; ++g) s += v[g];                                                       // CTA order
+      C[int64_t(ok[i]) * ldc + of[i]] = s;
     }
   }
   if (threadIdx.x == 0) *counter = 0;
 }
 
 static int tn_ctas(int64_t n) {
-  int64_t g = ceil_div(n, 64);
-  if (g > 148) g = 148;
+  int64_t g = ceil_div(n, 256);
+  if (g > kTnMaxCtas) g = kTnMaxCtas;
   return int(g < 1 ? 1 : g);
 }
 

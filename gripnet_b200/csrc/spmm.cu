@@ -18,7 +18,7 @@ namespace gn {
 // Y_{l+1} = H_l W_{l+1} in the forward pass (gripnet/layers.py:73 of the next conv), the PREVIOUS layer's
 // gradient dH_{l-1} = dY_l W_l^T (+ concat-slice gradient, ReLU mask) in the backward pass.  For the narrow
 // layers of the pose family (F * N2 <= 1024) this removes a GEMM launch from the step's dependency chain and an
-// [N, F] round trip through memory.  W is staged once per CTA in shared memory as Ws[k][j].
+// [N, F] round trip through memory.  W (<= 4 KB) is read through L1.
 constexpr int kFuseMaxElems = 1024;
 struct SpmmFuse {
   const float* W;        // NULL: no fused transform
@@ -31,18 +31,10 @@ struct SpmmFuse {
 };
 
 template <int LPE, int VEC, bool FUSE>
-__global__ void __launch_bounds__(256, (FUSE ? 4 : (LPE == 16 ? 5 : 6))) spmm_kernel(
+__global__ void __launch_bounds__(256, (FUSE ? 5 : (LPE == 16 ? 5 : 6))) spmm_kernel(
     const gn_csr csr, const float* __restrict__ x, int64_t ldx, int F, const float* __restrict__ row_scale,
     const float* __restrict__ bias, const float* addend, int64_t ld_addend, int relu, float* out, int64_t ldo,
     float* __restrict__ partial, const SpmmFuse fuse) {
-  __shared__ float Ws[FUSE ? kFuseMaxElems : 1];
-  if (FUSE) {
-    for (int i = threadIdx.x; i < F * fuse.n2; i += blockDim.x) {
-      const int k = i / fuse.n2, j = i - k * fuse.n2;
-      Ws[i] = __ldg(fuse.W + (fuse.transW ? int64_t(j) * fuse.ldw + k : int64_t(k) * fuse.ldw + j));
-    }
-    __syncthreads();
-  }
   ChunkInfo ci;
   if (!chunk_info(csr, ci)) return;
   constexpr int EPI = 32 / LPE;
@@ -105,8 +97,14 @@ __global__ void __launch_bounds__(256, (FUSE ? 4 : (LPE == 16 ? 5 : 6))) spmm_ke
     if (!done) return;
     // y2[j] = sum_k h[k] Ws[k][j]: lane j (and j + 32) owns an output column, h[k] is broadcast from the slot-0
     // lane that holds it (feature lane k / VEC, component k % VEC)
+    // W (<= 4 KB) is read through L1: after the first rows of a CTA every access is a hit, and there is no
+    // staging step or barrier in front of the gather loop
     float y0 = 0.f, y1 = 0.f;
     const int n2 = fuse.n2;
+    const int64_t sk = fuse.transW ? 1 : fuse.ldw, sj = fuse.transW ? fuse.ldw : 1;
+    const float* w0 = fuse.W + int64_t(lane) * sj;
+    const float* w1 = fuse.W + int64_t(lane + 32) * sj;
+    const bool has0 = lane < n2, has1 = lane + 32 < n2;
 #pragma unroll
     for (int l = 0; l < LPE; ++l) {
 #pragma unroll
@@ -114,8 +112,8 @@ __global__ void __launch_bounds__(256, (FUSE ? 4 : (LPE == 16 ? 5 : 6))) spmm_ke
         const float hk = __shfl_sync(kFull, acc[0].v[i], l);
         const int k = l * VEC + i;
         if (k < F) {
-          if (lane < n2) y0 = fmaf(hk, Ws[k * n2 + lane], y0);
-          if (lane + 32 < n2) y1 = fmaf(hk, Ws[k * n2 + lane + 32], y1);
+          if (has0) y0 = fmaf(hk, __ldg(w0 + k * sk), y0);
+          if (has1) y1 = fmaf(hk, __ldg(w1 + k * sk), y1);
         }
       }
     }

@@ -10,6 +10,7 @@ PyTorch is used for device memory (``torch.empty``) and streams only; every
 arithmetic step is a kernel of ``libgripnet_b200.so``.
 """
 import os
+import weakref
 
 import torch
 
@@ -180,12 +181,15 @@ def rel_transform(x, w, y, r, k, f, device):
     sgemm(False, False, n, f, k, x.ptr, x.ld, w.data_ptr(), f, y.ptr, y.ld, device, batch=r, sa=0, sb=k * f, sc=f)
 
 
+_TN_MAX_ROWS = 1 << 17      # beyond this the split-K GEMM's many CTAs stream the operands faster
+
+
 def weight_grad(a, b, out, device):
     """``out[K, F] = a^T b`` (``a``: M [n, K], ``b``: M [n, F]; the reduction runs over the nodes): the one-launch
     tall-skinny kernel for the narrow layers, the generic split-K GEMM otherwise."""
     lib = _lib.load()
     k, f, n = a.f, b.f, a.n
-    if lib.gn_tn_gemm_ok(k, f):
+    if lib.gn_tn_gemm_ok(k, f) and n <= _TN_MAX_ROWS:
         ws = _ws(lib.gn_tn_gemm_workspace_bytes(n, k, f), device)
         _lib.check(lib.gn_tn_gemm(a.ptr, a.ld, b.ptr, b.ld, n, k, f, out.data_ptr(), f, _ptr(ws), ws.numel(),
                                   _stream()), "gn_tn_gemm")
@@ -272,6 +276,7 @@ class GcnStack(torch.autograd.Function):
         br.join()
         ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
         ctx.has_bias = [b is not None for b in biases]
+        ctx.param_refs = [None if p is None else weakref.ref(p) for p in params]
         ws = [w.contiguous() for w in weights]
         # outputs/intermediates go through save_for_backward (no ctx <-> output reference cycle)
         acts = [buf] if catout else [o.t for o in outs]
@@ -357,8 +362,16 @@ class GcnStack(torch.autograd.Function):
                     dz_slot = dprev
                 if l == 1:
                     dx0 = dprev.m.t
-        br.join()
+        br.join(deferrable=_only_stored(ctx, dctx))
         return (dx0, None, None, None) + tuple(grads)
+
+
+def _only_stored(ctx, dctx):
+    """May the parameter-gradient branch of this backward stay un-joined until the backward pass ends?"""
+    if dctx is not None and not dctx.defer_grad_reduce:
+        return False                      # the gradients are all-reduced right away
+    params = [None if r is None else r() for r in ctx.param_refs]
+    return streams.grads_only_stored(params, ctx.needs_input_grad[4:])
 
 
 # ----------------------------------------------------------------------------
@@ -428,6 +441,7 @@ class RgcnStack(torch.autograd.Function):
         br.join()
         ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
         ctx.has_bias = [b is not None for b in bias]
+        ctx.param_refs = [None if p is None else weakref.ref(p) for p in params]
         acts = [buf] if catout else [o.t for o in outs]
         ctx.n_acts = len(acts)
         flat = [t for tup in ws_list for t in tup]
@@ -527,7 +541,7 @@ class RgcnStack(torch.autograd.Function):
                     dz_slot = dps
                 if l == 1:
                     dx0 = dprev.t
-        br.join()
+        br.join(deferrable=_only_stored(ctx, dctx))
         return (dx0, None, None, None) + tuple(grads)
 
 
@@ -705,7 +719,7 @@ class DistMult(torch.autograd.Function):
     def forward(ctx, z, weight, edge_index, edge_type, sigmoid):
         from .graph import pair_struct
         z, w, ei, et = _distmult_check(z, weight, edge_index, edge_type)
-        need = torch.is_grad_enabled() and (z.requires_grad or weight.requires_grad)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]      # (grad mode is off inside forward)
         br = streams.Branch()
         if need:      # the (node, relation) structure depends on the indices only: built next to the scores
             with br(edge_index, edge_type):
@@ -745,7 +759,7 @@ class DistMultPair(torch.autograd.Function):
         from .graph import pair_struct
         z, w, pi, et = _distmult_check(z, weight, pos_index, edge_type)
         _, _, ni, _ = _distmult_check(z, weight, neg_index, edge_type)
-        need = torch.is_grad_enabled() and (z.requires_grad or weight.requires_grad)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]      # (grad mode is off inside forward)
         br, br_s = streams.Branch(), streams.Branch()
         if need:
             with br_s(pos_index, neg_index, edge_type):

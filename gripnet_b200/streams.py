@@ -30,7 +30,10 @@ import threading
 import torch
 
 ENABLED = os.environ.get("GRIPNET_B200_STREAMS", "1") != "0"
-_N_SIDE = 4
+# parameter-gradient branches may stay un-joined until the END of the autograd backward pass (see
+# ``Branch.join(deferrable=True)``); "0" joins every branch where it was forked
+DEFER_JOINS = os.environ.get("GRIPNET_B200_DEFER_JOINS", "1") != "0"
+_N_SIDE = 8
 _tls = threading.local()
 _pools = {}
 _pool_lock = threading.Lock()
@@ -109,7 +112,16 @@ class Branch:
             _tls.side, _tls.branch = self._prev
         return False
 
-    def join(self):
+    def join(self, deferrable=False):
+        """Order the caller's stream behind the side work.  ``deferrable``: the results are parameter gradients
+        that nothing reads before the backward pass ends (the caller has checked that autograd will only STORE
+        them): the join is postponed to an autograd-engine callback that runs when the whole backward pass is
+        done, so the dependency chain of the step never waits for weight-gradient kernels."""
+        if deferrable and self.enabled and self._dirty and self._parent is None and DEFER_JOINS and _defer(self):
+            return
+        self._join_now()
+
+    def _join_now(self):
         if self.enabled and self._dirty:
             ev = torch.cuda.Event()
             ev.record(self.side)
@@ -120,3 +132,44 @@ class Branch:
             # alive until the parent joins the stream that allocated them
             self._parent._keep.extend(self._keep)
         self._keep.clear()
+
+
+# ---- joins deferred to the end of the autograd backward pass -------------------------------------------------
+_deferred = []
+_deferred_lock = threading.Lock()
+_callback_queued = [False]
+
+
+def _drain_deferred():
+    with _deferred_lock:
+        items = list(_deferred)
+        _deferred.clear()
+        _callback_queued[0] = False
+    for b in items:
+        b._join_now()
+
+
+def _defer(branch):
+    """Queue ``branch`` for the end-of-backward callback; False when no backward pass is running."""
+    with _deferred_lock:
+        need_cb = not _callback_queued[0]
+        if need_cb:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(_drain_deferred)
+            except RuntimeError:          # not inside a backward pass
+                return False
+            _callback_queued[0] = True
+        _deferred.append(branch)
+    return True
+
+
+def grads_only_stored(params, needs):
+    """True when every parameter of ``params`` that needs a gradient is a leaf whose ``.grad`` is still None:
+    autograd's AccumulateGrad will then just keep the tensor it is handed (no kernel reads it), so the kernels
+    that produce it may still be running on a side stream when ``backward()`` returns to the engine."""
+    for p, need in zip(params, needs):
+        if not need or p is None:
+            continue
+        if not p.is_leaf or p.grad is not None:
+            return False
+    return True
