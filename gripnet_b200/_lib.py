@@ -71,15 +71,9 @@ SIGNATURES = {
     "gn_index_prep_workspace_bytes": (_SZ, [_I64, _I32]),
     "gn_index_prep": (_INT, [_P, _I64, _I32, _P, _P, _P, _SZ, _P]),
     "gn_spmm": (_INT, [_CSR, _P, _I64, _I32, _P, _P, _P, _I64, _INT, _P, _I64, _P, _P]),
-    "gn_spmm_fused_ok": (_INT, [_I32, _I32]),
-    "gn_spmm_fused": (_INT, [_CSR, _P, _I64, _I32, _P, _P, _P, _I64, _INT, _P, _I64, _P, _P, _I32, _I64, _INT, _P,
-                             _I64, _P, _I64, _P, _I64, _P]),
     "gn_sgemm_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32, _INT]),
     "gn_sgemm": (_INT, [_INT, _INT, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _I32, _I64, _I64, _I64, _INT,
                         _F, _INT, _P, _I64, _P, _I64, _P, _I32, _P, _SZ, _P]),
-    "gn_tn_gemm_ok": (_INT, [_I32, _I32]),
-    "gn_tn_gemm_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
-    "gn_tn_gemm": (_INT, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _P, _SZ, _P]),
     "gn_tc_gemm_workspace_bytes": (_SZ, [_I32, _I32, _I32]),
     "gn_tc_gemm": (_INT, [_INT, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _SZ, _P]),
     "gn_tc_gemm_rel_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),

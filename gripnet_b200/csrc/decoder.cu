@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256) pair_walk_kernel(const gn_csr csr, const 
 }
 
 // dz / dw from T (and an optional second T of another edge list).  One CTA per output row: blocks
-// [0, n_nodes) form dz[n] = sum_r T[n,r] .* w[r], blocks [n_nodes, n_nodes + n_rel) form
-// dw[r] = 1/2 sum_n z[n] .* T[n,r].  The CTA's threads are G groups of D columns; group g adds the terms
+// [0, n_rel) form dw[r] = 1/2 sum_n z[n] .* T[n,r], blocks [n_rel, n_rel + n_nodes) form
+// dz[n] = sum_r T[n,r] .* w[r].  The CTA's threads are G groups of D columns; group g adds the terms
 // i = g, g + G, ... in order, then the G partial rows are added in group order: a fixed summation order.
 constexpr int kGradThreads = 1024;
 __global__ void __launch_bounds__(kGradThreads) distmult_grads_kernel(const float* __restrict__ T,
@@ -271,8 +271,9 @@ __global__ void __launch_bounds__(kGradThreads) distmult_grads_kernel(const floa
                                                                      float* __restrict__ dw) {
   extern __shared__ float red[];                       // [G][D]
   const int G = kGradThreads / D > 0 ? kGradThreads / D : 1;
-  const bool is_dz = int(blockIdx.x) < n_nodes;
-  const int row = is_dz ? int(blockIdx.x) : int(blockIdx.x) - n_nodes;
+  // the dw rows (n_nodes terms each) are the long ones: they take the FIRST blocks so they start first
+  const bool is_dz = int(blockIdx.x) >= n_rel;
+  const int row = is_dz ? int(blockIdx.x) - n_rel : int(blockIdx.x);
   const int n_terms = is_dz ? n_rel : n_nodes;
   if (is_dz ? dz == nullptr : dw == nullptr) return;
   for (int f0 = 0; f0 < D; f0 += kGradThreads) {       // D > 1024: column panels (G == 1)
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(kGradThreads) distmult_grads_kernel(const floa
     if (g < G && f < D) {
       // kU terms per round: every load of the round is issued before the first add (the terms are L2 / HBM
       // round trips), the adds stay in term order
-      constexpr int kU = 6;
+      constexpr int kU = 8;
       for (int i0 = g; i0 < n_terms; i0 += kU * G) {
         float tv[kU], ov[kU];
 #pragma unroll

@@ -304,143 +304,3 @@ extern "C" int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
   }
   return GN_OK;
 }
-
-// ---------------------------------------------------------------------------------------------------
-// Tall-skinny TN product for the weight gradients of the narrow layers:  C[K, F] = A^T B,  A: [n, K],
-// B: [n, F], K * F <= kTnMaxOut, n = number of nodes (the reduction).  dW = H_{l-1}^T dY of
-// gripnet/layers.py:73 under autograd.  ONE launch: every CTA reduces its slab of rows into a private
-// [K, F] partial (operands staged through shared memory with 128-bit loads), the partials go to `ws`, and the
-// LAST CTA to arrive (integer arrival counter) adds them in CTA order — a fixed summation order, so the
-// result is bit-reproducible — instead of the generic split-K kernel plus its separate reduce launch
-// (18-21 us + 25 us at pose-0 size, at the tail of the backward pass).
-// ---------------------------------------------------------------------------------------------------
-namespace gn {
-
-constexpr int kTnMaxOut = 2048;        // outputs per product: <= 8 accumulators per thread
-constexpr int kTnRows = 32;            // rows per staged tile
-constexpr int kTnMaxAcc = kTnMaxOut / 256;
-constexpr int kTnMaxCtas = 32;         // few partials: the last CTA's ordered sum stays a handful of round trips
-
-__global__ void __launch_bounds__(256) tn_gemm_kernel(const float* __restrict__ A, int64_t lda,
-                                                      const float* __restrict__ B, int64_t ldb, int64_t n, int K, int F,
-                                                      int rows_per_cta, float* __restrict__ C, int64_t ldc,
-                                                      float* __restrict__ partial, unsigned int* __restrict__ counter) {
-  extern __shared__ float tn_smem[];
-  float* As = tn_smem;                    // [kTnRows][K]
-  float* Bs = tn_smem + kTnRows * K;      // [kTnRows][F]
-  __shared__ int s_last;
-  const int n_out = K * F;
-  const int64_t r0 = int64_t(blockIdx.x) * rows_per_cta;
-  const int64_t r1 = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
-  // two accumulators per output (even / odd rows of a tile) halve the dependent FMA chain; they are added
-  // in a fixed order, so the result does not depend on timing
-  float acc0[kTnMaxAcc], acc1[kTnMaxAcc];
-  int ok[kTnMaxAcc], of[kTnMaxAcc];
-#pragma unroll
-  for (int i = 0; i < kTnMaxAcc; ++i) {
-    acc0[i] = acc1[i] = 0.f;
-    const int o = int(threadIdx.x) + 256 * i;
-    ok[i] = o < n_out ? o / F : -1;
-    of[i] = o < n_out ? o - (o / F) * F : 0;
-  }
-  const bool vec = (K % 4 == 0) && (F % 4 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) &&
-                   ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
-  for (int64_t t0 = r0; t0 < r1; t0 += kTnRows) {
-    const int rows = int(r1 - t0 < kTnRows ? r1 - t0 : kTnRows);
-    if (vec) {
-      const int k4 = K / 4, f4 = F / 4;
-      for (int i = threadIdx.x; i < kTnRows * k4; i += 256) {
-        const int r = i / k4, c = i - r * k4;
-        *reinterpret_cast<float4*>(As + r * K + 4 * c) =
-            r < rows ? ldg4(A + (t0 + r) * lda + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      for (int i = threadIdx.x; i < kTnRows * f4; i += 256) {
-        const int r = i / f4, c = i - r * f4;
-        *reinterpret_cast<float4*>(Bs + r * F + 4 * c) =
-            r < rows ? ldg4(B + (t0 + r) * ldb + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    } else {
-      for (int i = threadIdx.x; i < kTnRows * K; i += 256) As[i] = i / K < rows ? __ldg(A + (t0 + i / K) * lda + i % K) : 0.f;
-      for (int i = threadIdx.x; i < kTnRows * F; i += 256) Bs[i] = i / F < rows ? __ldg(B + (t0 + i / F) * ldb + i % F) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < kTnMaxAcc; ++i) {
-      if (ok[i] >= 0) {
-        const float* ap = As + ok[i];
-        const float* bp = Bs + of[i];
-        float a0 = acc0[i], a1 = acc1[i];
-#pragma unroll 8
-        for (int r = 0; r < kTnRows; r += 2) {     // rows past the slab are zero-filled
-          a0 = fmaf(ap[r * K], bp[r * F], a0);
-          a1 = fmaf(ap[(r + 1) * K], bp[(r + 1) * F], a1);
-        }
-        acc0[i] = a0;
-        acc1[i] = a1;
-      }
-    }
-    __syncthreads();
-  }
-  float* mine = partial + int64_t(blockIdx.x) * n_out;
-#pragma unroll
-  for (int i = 0; i < kTnMaxAcc; ++i)
-    if (ok[i] >= 0) mine[int(threadIdx.x) + 256 * i] = acc0[i] + acc1[i];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int G = gridDim.x;
-#pragma unroll
-  for (int i = 0; i < kTnMaxAcc; ++i) {
-    if (ok[i] >= 0) {
-      const int o = int(threadIdx.x) + 256 * i;
-      float v[kTnMaxCtas];
-#pragma unroll
-      for (int g = 0; g < kTnMaxCtas; ++g) v[g] = g < G ? __ldcg(partial + int64_t(g) * n_out + o) : 0.f;   // all in flight
-      float s = 0.f;
-#pragma unroll
-      for (int g = 0; g < kTnMaxCtas; ++g) s += v[g];                                                       // CTA order
-      C[int64_t(ok[i]) * ldc + of[i]] = s;
-    }
-  }
-  if (threadIdx.x == 0) *counter = 0;
-}
-
-static int tn_ctas(int64_t n) {
-  int64_t g = ceil_div(n, 256);
-  if (g > kTnMaxCtas) g = kTnMaxCtas;
-  return int(g < 1 ? 1 : g);
-}
-
-}  // namespace gn
-
-extern "C" int gn_tn_gemm_ok(int32_t K, int32_t F) {
-  return (K > 0 && F > 0 && int64_t(K) * F <= gn::kTnMaxOut && (K + F) * gn::kTnRows * 4 <= 48 * 1024) ? 1 : 0;
-}
-
-extern "C" size_t gn_tn_gemm_workspace_bytes(int64_t n, int32_t K, int32_t F) {
-  return 256 + size_t(gn::tn_ctas(n)) * size_t(K) * size_t(F) * 4;
-}
-
-extern "C" int gn_tn_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t K, int32_t F,
-                          float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream) {
-  if (n < 0 || !gn_tn_gemm_ok(K, F) || !C) return GN_ERR_ARG;
-  cudaStream_t st = gn::as_stream(stream);
-  if (n == 0) {
-    if (cudaMemset2DAsync(C, size_t(ldc) * 4, 0, size_t(F) * 4, size_t(K), st) != cudaSuccess) return GN_ERR_CUDA;
-    return GN_OK;
-  }
-  if (!A || !B) return GN_ERR_ARG;
-  if (!ws || ws_bytes < gn_tn_gemm_workspace_bytes(n, K, F) || (reinterpret_cast<uintptr_t>(ws) & 15)) return GN_ERR_WORKSPACE;
-  const int G = gn::tn_ctas(n);
-  const int rows_per_cta = int(gn::ceil_div(n, G));
-  unsigned int* counter = static_cast<unsigned int*>(ws);
-  float* partial = reinterpret_cast<float*>(static_cast<char*>(ws) + 256);
-  if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return GN_ERR_CUDA;
-  const size_t smem = size_t(K + F) * gn::kTnRows * sizeof(float);
-  GN_LAUNCH(gn::tn_gemm_kernel, (unsigned)G, 256, smem, st, A, lda, B, ldb, n, K, F, rows_per_cta, C, ldc, partial,
-            counter);
-  return GN_OK;
-}

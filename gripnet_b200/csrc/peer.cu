@@ -5,13 +5,13 @@
 // The producing kernel wrote this rank's slot in place; this kernel
 //   1. PUSHES the slot into every peer's buffer with 128-bit stores over NVLink (one local read,
 //      world-1 remote writes per vector, peers visited in a rank-staggered order),
-//   2. the last CTA to finish publishes "rank r has delivered buffer b, use e" in every peer's
-//      flag block (fence.sys + st.release.sys), and
-//   3. waits (ld.acquire.sys on its OWN flag block) until every peer has delivered, so the SpMM
-//      that follows on the stream sees the complete operand.
+//   2. every CTA, once its stores are issued, adds 1 to "CTAs of rank r that delivered buffer b" in every
+//      peer's flag block (fence.sys + remote red.release.sys), and
+//   3. CTA 0 waits (ld.acquire.sys on its OWN flag block) until every peer's count is complete, so the
+//      SpMM that follows on the stream sees the complete operand.
 // No host synchronisation, no NCCL, CUDA-graph capturable: the use counter `e` lives in device
-// memory, so a replayed graph keeps counting.  Deadlock-free: every rank publishes before it
-// waits, and only one thread per rank spins.
+// memory, so a replayed graph keeps counting.  Deadlock-free: signalling never waits, and only
+// one CTA per rank spins.
 //
 // Buffer reuse: a buffer (arena offset) is used once per step.  A peer can only be writing use
 // e+1 of buffer b into this rank while this rank still reads use e if it ran a whole step ahead,
@@ -26,6 +26,7 @@ constexpr int kMaxPeers = 8;
 struct PeerArgs {
   char* buf[kMaxPeers];                  // every rank's gather buffer (peer-mapped device pointers)
   unsigned long long* flags[kMaxPeers];  // every rank's flag block: [n_buffers][kMaxPeers]
+  char* mc;                              // multicast (NVLS) mapping of the same buffer on ALL ranks, or NULL
   int world, rank;
   int64_t slot_bytes;
   int flag_index;
@@ -43,39 +44,60 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// Every CTA has issued its stores: the LAST CTA publishes "rank r has delivered buffer b, use e" in every
-// peer's flag block and waits until every peer has published the same for this rank.
+// one store, delivered by the NVSwitch to the same offset of every rank's buffer (this rank's included)
+__device__ __forceinline__ void multimem_st16(void* p, const int4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__int_as_float(v.x)),
+               "f"(__int_as_float(v.y)), "f"(__int_as_float(v.z)), "f"(__int_as_float(v.w))
+               : "memory");
+}
+
+__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Publish / wait round of one exchange.  Flag (buffer b, rank r) in a rank's flag block COUNTS the CTAs of rank
+// r that have delivered their part of buffer b, over all uses of the buffer (u64, never reset).
+//   * every CTA: once its own stores are issued (barrier), ONE thread orders them system-wide (fence.sys, cumulative
+//     over the CTA's stores through the barrier) and adds 1 to its flag in every peer's block with a remote
+//     red.release.sys — no intra-GPU arrival counter, no serial "last CTA" tail: a CTA's signal leaves as soon as
+//     that CTA is done;
+//   * CTA 0 alone waits: thread p spins (ld.acquire.sys on this rank's OWN memory) until peer p's count reaches
+//     (uses so far + 1) x gridDim.x — every rank launches the same grid for the same buffer, because buffer shapes
+//     are symmetric.  The kernel therefore ends only when every peer's data has arrived, and the kernels behind it
+//     on the stream see the complete buffer.
+// Deadlock-free: signalling never waits, and only one CTA per rank spins (bounded, see below).
 __device__ __forceinline__ void signal_and_wait(const PeerArgs& a) {
-  __threadfence_system();
+  __shared__ unsigned long long s_use;
   __syncthreads();
-  if (threadIdx.x != 0) return;
-  const unsigned int prev = atomicAdd(a.done, 1u);
-  if (prev != gridDim.x - 1) return;
-  // last CTA: every CTA's pushes are ordered before this point (fence + atomic on each side)
-  __threadfence_system();
-  *a.done = 0;
-  const unsigned long long e = *a.seq + 1;
-  *a.seq = e;
   const int slot = a.flag_index * kMaxPeers;
-  for (int s = 1; s < a.world; ++s) {
-    const int peer = (a.rank + s) % a.world;
-    st_release_sys(a.flags[peer] + slot + a.rank, e);
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int s = 1; s < a.world; ++s) {
+      const int peer = (a.rank + s) % a.world;
+      red_release_sys_add(a.flags[peer] + slot + a.rank, 1ull);
+    }
   }
-  for (int s = 1; s < a.world; ++s) {
-    const int peer = (a.rank + s) % a.world;
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x == 0) s_use = *a.seq + 1;
+  __syncthreads();
+  const unsigned long long target = s_use * gridDim.x;
+  if (threadIdx.x >= 1 && threadIdx.x < a.world) {
+    const int peer = (a.rank + int(threadIdx.x)) % a.world;
     const unsigned long long* f = a.flags[a.rank] + slot + peer;
     // bounded spin (~10 s): a rank that died must not hang this GPU.  A timeout raises the abort
     // flag: results are then visibly wrong (the host checks the flag) instead of the GPU being stuck.
     unsigned int spins = 0;
-    while (ld_acquire_sys(f) < e) {
-      if (*reinterpret_cast<volatile unsigned int*>(a.abort_flag) != 0) return;
-      __nanosleep(256);
-      if (++spins > (1u << 23)) {
+    while (ld_acquire_sys(f) < target) {
+      if (*reinterpret_cast<volatile unsigned int*>(a.abort_flag) != 0) break;
+      __nanosleep(64);
+      if (++spins > (1u << 25)) {
         *reinterpret_cast<volatile unsigned int*>(a.abort_flag) = 1;
-        return;
+        break;
       }
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) *a.seq = s_use;
 }
 
 __global__ void __launch_bounds__(256) peer_allgather_kernel(const PeerArgs a) {
@@ -85,10 +107,14 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(const PeerArgs a) {
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
     const int4 v = src[i];
+    if (a.mc != nullptr) {                 // NVLS: one store leaves the GPU, the switch replicates it
+      multimem_st16(a.mc + slot_off + i * 16, v);
+    } else {
 #pragma unroll 1
-    for (int s = 1; s < a.world; ++s) {
-      const int peer = (a.rank + s) % a.world;
-      reinterpret_cast<int4*>(a.buf[peer] + slot_off)[i] = v;
+      for (int s = 1; s < a.world; ++s) {
+        const int peer = (a.rank + s) % a.world;
+        reinterpret_cast<int4*>(a.buf[peer] + slot_off)[i] = v;
+      }
     }
   }
   signal_and_wait(a);
@@ -140,6 +166,10 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const PeerArgs a, const 
       const int64_t i = base + (int64_t(it) * 256 + threadIdx.x) * 16;
       if (i >= bytes) break;
       const int4 v = *reinterpret_cast<const int4*>(src + i);
+      if (b.peer[s] < 0 && a.mc != nullptr) {
+        multimem_st16(a.mc + dst_off + i, v);
+        continue;
+      }
       for (int q = p_first; q <= p_last; ++q) {
         const int peer = (b.peer[s] < 0) ? (a.rank + q) % a.world : q;     // staggered start: not everyone hits rank 0 first
         *reinterpret_cast<int4*>(a.buf[peer] + dst_off + i) = v;
@@ -209,25 +239,17 @@ using namespace gn;
 
 extern "C" int gn_peer_max_world(void) { return kMaxPeers; }
 
+static int fill_peer_args(PeerArgs& a, const uint64_t* arena_base, int32_t world, int32_t rank, int64_t buf_offset,
+                          int64_t slot_bytes, int64_t flag_offset, int32_t flag_index, uint64_t* seq, uint32_t* done,
+                          uint32_t* abort_flag);
+
 extern "C" int gn_peer_allgather(const uint64_t* arena_base /*host*/, int32_t world, int32_t rank, int64_t buf_offset,
                                  int64_t slot_bytes, int64_t flag_offset, int32_t flag_index, uint64_t* seq,
                                  uint32_t* done, uint32_t* abort_flag, void* stream) {
-  if (!arena_base || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || slot_bytes < 0 || flag_index < 0 ||
-      !seq || !done || !abort_flag)
-    return GN_ERR_ARG;
-  if (slot_bytes % 16 != 0 || buf_offset % 16 != 0 || flag_offset % 8 != 0) return GN_ERR_ARG;
   if (world == 1) return GN_OK;
   PeerArgs a;
-  for (int p = 0; p < kMaxPeers; ++p) {
-    const uint64_t base = p < world ? arena_base[p] : 0;
-    if (p < world && base == 0) return GN_ERR_ARG;
-    a.buf[p] = reinterpret_cast<char*>(base + (p < world ? uint64_t(buf_offset) : 0));
-    a.flags[p] = reinterpret_cast<unsigned long long*>(base + (p < world ? uint64_t(flag_offset) : 0));
-  }
-  a.world = world; a.rank = rank; a.slot_bytes = slot_bytes; a.flag_index = flag_index;
-  a.seq = reinterpret_cast<unsigned long long*>(seq);
-  a.done = done;
-  a.abort_flag = abort_flag;
+  GN_CHECK(fill_peer_args(a, arena_base, world, rank, buf_offset, slot_bytes, flag_offset, flag_index, seq, done,
+                          abort_flag));
   // enough CTAs to keep the NVLink ports busy, few enough that the arrival counter is cheap
   int64_t ctas = ceil_div((slot_bytes >> 4) > 0 ? (slot_bytes >> 4) : 1, 256 * 4);
   if (ctas > 148 * 2) ctas = 148 * 2;
@@ -249,6 +271,7 @@ static int fill_peer_args(PeerArgs& a, const uint64_t* arena_base, int32_t world
     a.buf[p] = reinterpret_cast<char*>(base + (p < world ? uint64_t(buf_offset) : 0));
     a.flags[p] = reinterpret_cast<unsigned long long*>(base + (p < world ? uint64_t(flag_offset) : 0));
   }
+  a.mc = arena_base[world] ? reinterpret_cast<char*>(arena_base[world] + uint64_t(buf_offset)) : nullptr;
   a.world = world; a.rank = rank; a.slot_bytes = slot_bytes; a.flag_index = flag_index;
   a.seq = reinterpret_cast<unsigned long long*>(seq);
   a.done = done;

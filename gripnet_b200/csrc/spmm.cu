@@ -13,28 +13,11 @@
 
 namespace gn {
 
-// Fused row transform (SpMM epilogue): while the finished output row h (F floats) is still in registers the warp
-// also forms  y2 = h . op(W) (+ addend2) (zeroed where mask2 <= 0)  — the NEXT layer's dense transform
-// Y_{l+1} = H_l W_{l+1} in the forward pass (gripnet/layers.py:73 of the next conv), the PREVIOUS layer's
-// gradient dH_{l-1} = dY_l W_l^T (+ concat-slice gradient, ReLU mask) in the backward pass.  For the narrow
-// layers of the pose family (F * N2 <= 1024) this removes a GEMM launch from the step's dependency chain and an
-// [N, F] round trip through memory.  W (<= 4 KB) is read through L1.
-constexpr int kFuseMaxElems = 1024;
-struct SpmmFuse {
-  const float* W;        // NULL: no fused transform
-  int n2;                // output width of the transform (<= 64)
-  int ldw;
-  int transW;            // 0: op(W)[k][j] = W[k*ldw + j]   1: op(W)[k][j] = W[j*ldw + k]
-  float* y2; int64_t ldy2;
-  const float* addend2; int64_t lda2;
-  const float* mask2; int64_t ldm2;
-};
-
-template <int LPE, int VEC, bool FUSE>
-__global__ void __launch_bounds__(256, (FUSE ? 5 : (LPE == 16 ? 5 : 6))) spmm_kernel(
+template <int LPE, int VEC>
+__global__ void __launch_bounds__(256, (LPE == 16 ? 5 : 6)) spmm_kernel(
     const gn_csr csr, const float* __restrict__ x, int64_t ldx, int F, const float* __restrict__ row_scale,
     const float* __restrict__ bias, const float* addend, int64_t ld_addend, int relu, float* out, int64_t ldo,
-    float* __restrict__ partial, const SpmmFuse fuse) {
+    float* __restrict__ partial) {
   ChunkInfo ci;
   if (!chunk_info(csr, ci)) return;
   constexpr int EPI = 32 / LPE;
@@ -90,59 +73,19 @@ __global__ void __launch_bounds__(256, (FUSE ? 5 : (LPE == 16 ? 5 : 6))) spmm_ke
       for (int i = 0; i < VEC; ++i) r.v[i] = fmaxf(r.v[i], 0.f);
     }
     store_vec<VEC>(out + int64_t(row) * ldo + ff, r);
-    if (FUSE) acc[0] = r;                       // the finished row stays in registers for the fused transform
   };
-  const bool done = finish_row<LPE, VEC, 1>(csr, ci, acc, F, partial, emit);
-  if (FUSE) {
-    if (!done) return;
-    // y2[j] = sum_k h[k] Ws[k][j]: lane j (and j + 32) owns an output column, h[k] is broadcast from the slot-0
-    // lane that holds it (feature lane k / VEC, component k % VEC)
-    // W (<= 4 KB) is read through L1: after the first rows of a CTA every access is a hit, and there is no
-    // staging step or barrier in front of the gather loop
-    float y0 = 0.f, y1 = 0.f;
-    const int n2 = fuse.n2;
-    const int64_t sk = fuse.transW ? 1 : fuse.ldw, sj = fuse.transW ? fuse.ldw : 1;
-    const float* w0 = fuse.W + int64_t(lane) * sj;
-    const float* w1 = fuse.W + int64_t(lane + 32) * sj;
-    const bool has0 = lane < n2, has1 = lane + 32 < n2;
-#pragma unroll
-    for (int l = 0; l < LPE; ++l) {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float hk = __shfl_sync(kFull, acc[0].v[i], l);
-        const int k = l * VEC + i;
-        if (k < F) {
-          if (has0) y0 = fmaf(hk, __ldg(w0 + k * sk), y0);
-          if (has1) y1 = fmaf(hk, __ldg(w1 + k * sk), y1);
-        }
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = lane + 32 * h;
-      if (j < n2) {
-        float v = h ? y1 : y0;
-        if (fuse.addend2) v += fuse.addend2[int64_t(row) * fuse.lda2 + j];
-        if (fuse.mask2 && !(fuse.mask2[int64_t(row) * fuse.ldm2 + j] > 0.f)) v = 0.f;
-        fuse.y2[int64_t(row) * fuse.ldy2 + j] = v;
-      }
-    }
-  }
+  finish_row<LPE, VEC, 1>(csr, ci, acc, F, partial, emit);
 }
 
 template <int VEC>
 static int launch_spmm(int lpe, const gn_csr& csr, const float* x, int64_t ldx, int F, const float* row_scale,
                        const float* bias, const float* addend, int64_t ld_addend, int relu, float* out, int64_t ldo,
-                       float* partial, const SpmmFuse& fuse, cudaStream_t st) {
+                       float* partial, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
-#define GN_SPMM_CASE(L)                                                                                       \
-  case L:                                                                                                     \
-    if (fuse.W)                                                                                               \
-      GN_LAUNCH((spmm_kernel<L, VEC, true>), grid, 256, 0, st, csr, x, ldx, F, row_scale, bias, addend,       \
-                ld_addend, relu, out, ldo, partial, fuse);                                                    \
-    else                                                                                                      \
-      GN_LAUNCH((spmm_kernel<L, VEC, false>), grid, 256, 0, st, csr, x, ldx, F, row_scale, bias, addend,      \
-                ld_addend, relu, out, ldo, partial, fuse);                                                    \
+#define GN_SPMM_CASE(L)                                                                                  \
+  case L:                                                                                                \
+    GN_LAUNCH((spmm_kernel<L, VEC>), grid, 256, 0, st, csr, x, ldx, F, row_scale, bias, addend, ld_addend, \
+              relu, out, ldo, partial);                                                                  \
     break;
   switch (lpe) {
     GN_SPMM_CASE(1)
@@ -161,9 +104,9 @@ static int launch_spmm(int lpe, const gn_csr& csr, const float* x, int64_t ldx, 
 
 using namespace gn;
 
-static int spmm_impl(const gn_csr* csr, const float* x, int64_t ldx, int32_t F, const float* row_scale,
-                     const float* bias, const float* addend, int64_t ld_addend, int relu, float* out, int64_t ldo,
-                     float* partial, const SpmmFuse& fuse, void* stream) {
+extern "C" int gn_spmm(const gn_csr* csr, const float* x, int64_t ldx, int32_t F, const float* row_scale,
+                       const float* bias, const float* addend, int64_t ld_addend, int relu, float* out, int64_t ldo,
+                       float* partial, void* stream) {
   if (!csr || !x || !out || F <= 0 || !csr->rowptr || !csr->chunk_ptr || !csr->chunk_row || !csr->chunk_beg ||
       !csr->row_counter || csr->chunk_len <= 0)
     return GN_ERR_ARG;
@@ -174,47 +117,21 @@ static int spmm_impl(const gn_csr* csr, const float* x, int64_t ldx, int32_t F, 
   const bool vec4 = (F % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) && aligned16(out) &&
                     (!partial || aligned16(partial)) && (!bias || aligned16(bias)) &&
                     (!addend || (aligned16(addend) && ld_addend % 4 == 0));
-  if (fuse.W) {        // the fused transform needs the whole row in ONE launch, vectorised
-    if (!vec4 || F > 128 || fuse.n2 <= 0 || fuse.n2 > 64 || F * fuse.n2 > kFuseMaxElems || !fuse.y2) return GN_ERR_ARG;
-    return launch_spmm<4>(pow2_ceil(F / 4), *csr, x, ldx, F, row_scale, bias, addend, ld_addend, relu, out, ldo,
-                          partial, fuse, st);
-  }
   if (vec4) {
     // one launch covers up to 128 columns; wider rows are processed in 128-column panels
     for (int f0 = 0; f0 < F; f0 += 128) {
       const int w = F - f0 < 128 ? F - f0 : 128;
       const int lpe = pow2_ceil(w / 4);
       GN_CHECK(launch_spmm<4>(lpe, *csr, x + f0, ldx, w, row_scale, bias ? bias + f0 : nullptr,
-                              addend ? addend + f0 : nullptr, ld_addend, relu, out + f0, ldo, partial, fuse, st));
+                              addend ? addend + f0 : nullptr, ld_addend, relu, out + f0, ldo, partial, st));
     }
   } else {
     for (int f0 = 0; f0 < F; f0 += 32) {
       const int w = F - f0 < 32 ? F - f0 : 32;
       const int lpe = pow2_ceil(w);
       GN_CHECK(launch_spmm<1>(lpe, *csr, x + f0, ldx, w, row_scale, bias ? bias + f0 : nullptr,
-                              addend ? addend + f0 : nullptr, ld_addend, relu, out + f0, ldo, partial, fuse, st));
+                              addend ? addend + f0 : nullptr, ld_addend, relu, out + f0, ldo, partial, st));
     }
   }
   return GN_OK;
-}
-
-extern "C" int gn_spmm(const gn_csr* csr, const float* x, int64_t ldx, int32_t F, const float* row_scale,
-                       const float* bias, const float* addend, int64_t ld_addend, int relu, float* out, int64_t ldo,
-                       float* partial, void* stream) {
-  SpmmFuse fuse{};
-  return spmm_impl(csr, x, ldx, F, row_scale, bias, addend, ld_addend, relu, out, ldo, partial, fuse, stream);
-}
-
-extern "C" int gn_spmm_fused_ok(int32_t F, int32_t n2) {
-  return (F > 0 && F % 4 == 0 && F <= 128 && n2 > 0 && n2 <= 64 && F * n2 <= kFuseMaxElems) ? 1 : 0;
-}
-
-extern "C" int gn_spmm_fused(const gn_csr* csr, const float* x, int64_t ldx, int32_t F, const float* row_scale,
-                             const float* bias, const float* addend, int64_t ld_addend, int relu, float* out,
-                             int64_t ldo, float* partial, const float* W, int32_t n2, int64_t ldw, int transW,
-                             float* y2, int64_t ldy2, const float* addend2, int64_t ld_addend2,
-                             const float* relu_mask2, int64_t ld_mask2, void* stream) {
-  if (!W || !y2) return GN_ERR_ARG;
-  SpmmFuse fuse{W, n2, int(ldw), transW ? 1 : 0, y2, ldy2, addend2, ld_addend2, relu_mask2, ld_mask2};
-  return spmm_impl(csr, x, ldx, F, row_scale, bias, addend, ld_addend, relu, out, ldo, partial, fuse, stream);
 }

@@ -84,31 +84,9 @@ def _reduce(dctx, t):
 # ----------------------------------------------------------------------------
 # thin kernel wrappers
 # ----------------------------------------------------------------------------
-FUSE_TRANSFORMS = os.environ.get("GRIPNET_B200_FUSE", "1") != "0"
-
-
-def fuse_ok(F, n2, *views):
-    """Can a [*, F] SpMM fuse a F -> n2 row transform into its epilogue (``gn_spmm_fused``)?"""
-    if not FUSE_TRANSFORMS or not _lib.load().gn_spmm_fused_ok(int(F), int(n2)):
-        return False
-    return all(v is None or (v.ld % 4 == 0 and v.ptr % 16 == 0) for v in views)
-
-
-def spmm(csr, x, out, F, row_scale=None, bias=None, addend=None, relu=False, fuse=None):
-    """``fuse``: ``(W tensor [contiguous], n2, transW, y2 M, addend2 M or None, mask2 M or None)`` -> the row
-    transform ``y2 = out_row . op(W) (+ addend2)(mask2)`` rides in the SpMM's epilogue."""
+def spmm(csr, x, out, F, row_scale=None, bias=None, addend=None, relu=False):
     lib = _lib.load()
     partial = csr.partial(min(F, 128))
-    if fuse is not None:
-        w, n2, trans_w, y2, add2, mask2 = fuse
-        _lib.check(lib.gn_spmm_fused(csr.ref, x.ptr, x.ld, F, _ptr(row_scale), _ptr(bias),
-                                     addend.ptr if addend is not None else None,
-                                     addend.ld if addend is not None else 0, int(relu), out.ptr, out.ld,
-                                     _ptr(partial), w.data_ptr(), n2, w.size(1), int(trans_w), y2.ptr, y2.ld,
-                                     add2.ptr if add2 is not None else None, add2.ld if add2 is not None else 0,
-                                     mask2.ptr if mask2 is not None else None, mask2.ld if mask2 is not None else 0,
-                                     _stream()), "gn_spmm_fused")
-        return
     _lib.check(lib.gn_spmm(csr.ref, x.ptr, x.ld, F, _ptr(row_scale), _ptr(bias),
                            addend.ptr if addend is not None else None, addend.ld if addend is not None else 0,
                            int(relu), out.ptr, out.ld, _ptr(partial), _stream()), "gn_spmm")
@@ -181,22 +159,6 @@ def rel_transform(x, w, y, r, k, f, device):
     sgemm(False, False, n, f, k, x.ptr, x.ld, w.data_ptr(), f, y.ptr, y.ld, device, batch=r, sa=0, sb=k * f, sc=f)
 
 
-_TN_MAX_ROWS = 1 << 17      # beyond this the split-K GEMM's many CTAs stream the operands faster
-
-
-def weight_grad(a, b, out, device):
-    """``out[K, F] = a^T b`` (``a``: M [n, K], ``b``: M [n, F]; the reduction runs over the nodes): the one-launch
-    tall-skinny kernel for the narrow layers, the generic split-K GEMM otherwise."""
-    lib = _lib.load()
-    k, f, n = a.f, b.f, a.n
-    if lib.gn_tn_gemm_ok(k, f) and n <= _TN_MAX_ROWS:
-        ws = _ws(lib.gn_tn_gemm_workspace_bytes(n, k, f), device)
-        _lib.check(lib.gn_tn_gemm(a.ptr, a.ld, b.ptr, b.ld, n, k, f, out.data_ptr(), f, _ptr(ws), ws.numel(),
-                                  _stream()), "gn_tn_gemm")
-        return
-    sgemm(True, False, k, f, n, a.ptr, a.ld, b.ptr, b.ld, out.data_ptr(), f, device)
-
-
 def map2d(op, src, dst):
     _lib.check(_lib.load().gn_map2d(op, src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.f, _stream()), "gn_map2d")
 
@@ -247,31 +209,18 @@ class GcnStack(torch.autograd.Function):
         else:
             buf = None
             outs.append(M(x0))
-        y_next = None          # Y_l already produced by the previous layer's SpMM epilogue
         for l in range(n_layers):
             w = weights[l].contiguous()
             k, f = dims[l], dims[l + 1]
-            if y_next is not None:
-                y, y_next = y_next, None
-            else:
-                y = Slot(graph.n_src, f, x0, dctx, b_src)
-                xin = M(x0) if l == 0 else outs[l]
-                sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, y.m.ld, dev)
+            y = Slot(graph.n_src, f, x0, dctx, b_src)
+            xin = M(x0) if l == 0 else outs[l]
+            sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, y.m.ld, dev)
             if catout:
                 hl = M(buf, offs[l + 1], f)
             else:
                 hl = M(_new(graph.n_dst, f, x0))
             b = biases[l].contiguous() if biases[l] is not None else None
-            fuse = None
-            if l + 1 < n_layers and graph.n_src == graph.n_dst:
-                # the next layer's transform Y_{l+1} = H_{l+1} W_{l+1} rides in this SpMM's epilogue
-                f2 = dims[l + 2]
-                y_next = Slot(graph.n_src, f2, x0, dctx, b_src)
-                if fuse_ok(f, f2, hl, y_next.m):
-                    fuse = (weights[l + 1].contiguous(), f2, False, y_next.m, None, None)
-                else:
-                    y_next = None
-            spmm(graph.fwd, y.gather(), hl, f, bias=b, relu=relu_flags[l], fuse=fuse)
+            spmm(graph.fwd, y.gather(), hl, f, bias=b, relu=relu_flags[l])
             outs.append(hl)
         br.join()
         ctx.graph, ctx.relu_flags, ctx.catout, ctx.dims = graph, relu_flags, catout, dims
@@ -332,9 +281,16 @@ class GcnStack(torch.autograd.Function):
                     colsum(dz.m, db)
                 grads[2 * (l - 1) + 1] = _reduce(dctx, db)
             dy = M(_new(graph.n_src, f, g))
+            spmm(graph.bwd, dz.gather(), dy, f)
+            if ctx.needs_input_grad[4 + 2 * (l - 1)]:
+                dw = torch.empty((k, f), dtype=torch.float32, device=dev)
+                # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
+                with br(dy.t, h_prev.t):
+                    sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f,
+                          dev)
+                grads[2 * (l - 1)] = _reduce(dctx, dw)
             need_prev = (l > 1) or ctx.needs_input_grad[0]
-            dprev = addend = mask = None
-            fused = False
+            dz_slot = None
             if need_prev:
                 w = weights[l - 1]
                 addend = gs[l - 1] if catout else None
@@ -342,21 +298,8 @@ class GcnStack(torch.autograd.Function):
                 # dH_{l-1} = dY W^T (+ concat-slice grad) (masked by ReLU of layer l-1); when it is the
                 # next layer's dZ it is produced straight into that layer's gather slot
                 dprev = Slot(graph.n_src, k, g, dctx if mask is not None else None, b_dst)
-                fused = fuse_ok(f, k, dy, dprev.m, addend, mask)
-            # dY = A^T dZ; with `fused` the same kernel also writes dH_{l-1} from the row it just finished
-            spmm(graph.bwd, dz.gather(), dy, f,
-                 fuse=(w, k, True, dprev.m, addend, mask) if fused else None)
-            if ctx.needs_input_grad[4 + 2 * (l - 1)]:
-                dw = torch.empty((k, f), dtype=torch.float32, device=dev)
-                # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
-                with br(dy.t, h_prev.t):
-                    weight_grad(h_prev, dy, dw, dev)
-                grads[2 * (l - 1)] = _reduce(dctx, dw)
-            dz_slot = None
-            if need_prev:
-                if not fused:
-                    sgemm(False, True, graph.n_src, k, f, dy.ptr, dy.ld, w.data_ptr(), f, dprev.m.ptr, dprev.m.ld,
-                          dev, addend=addend, mask=mask)
+                sgemm(False, True, graph.n_src, k, f, dy.ptr, dy.ld, w.data_ptr(), f, dprev.m.ptr, dprev.m.ld, dev,
+                      addend=addend, mask=mask)
                 dh = dprev.m
                 if mask is not None:
                     dz_slot = dprev
@@ -505,7 +448,7 @@ class RgcnStack(torch.autograd.Function):
             if ctx.needs_input_grad[base + 2]:
                 droot = torch.empty((k, f), dtype=torch.float32, device=dev)
                 with br(dz.t, h_prev.t):
-                    weight_grad(h_prev, dz, droot, dev)
+                    sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dz.ptr, dz.ld, droot.data_ptr(), f, dev)
                 grads[4 * (l - 1) + 2] = _reduce(dctx, droot)
             if ctx.needs_input_grad[base] or ctx.needs_input_grad[base + 1]:
                 # dW[r] = H_{l-1}^T dY[:, r, :]

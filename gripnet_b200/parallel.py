@@ -27,6 +27,7 @@ import torch
 import torch.distributed as dist
 
 PEER_MODE = os.environ.get("GRIPNET_B200_PEER", "auto")     # "auto" | "off"
+MULTICAST = os.environ.get("GRIPNET_B200_MULTICAST", "1") != "0"
 
 
 class PeerArena:
@@ -55,7 +56,11 @@ class PeerArena:
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         if len(ptrs) != dctx.world or any(p == 0 for p in ptrs):
             raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
-        self.bases = (ctypes.c_uint64 * dctx.world)(*ptrs)
+        # last entry: the multicast (NVLS) mapping of the arena, when the fabric offers one — one store then
+        # reaches every rank (GRIPNET_B200_MULTICAST=0 keeps the unicast pushes)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if MULTICAST else 0
+        self.multicast = mc != 0
+        self.bases = (ctypes.c_uint64 * (dctx.world + 1))(*ptrs, mc)
         self.t[: self.flag_bytes].zero_()
         self.seq = torch.zeros(self.MAX_BUFFERS, dtype=torch.int64, device=dev)
         self.done = torch.zeros(self.MAX_BUFFERS, dtype=torch.int32, device=dev)

@@ -12,7 +12,8 @@ from torch.nn import Module, Parameter
 
 from . import parallel
 from .decoder import multiClassInnerProductDecoder, multiRelaInnerProductDecoder
-from . import ops
+from . import graph as G
+from . import ops, streams
 from .layers import homoGraph, interGraph
 from .losses import link_prediction_loss, node_classification_loss
 
@@ -42,15 +43,29 @@ class PoseModel(Module):
         dctx = data.get("dist")
         if dctx is not None:
             dctx.begin_step()
-        z = self.embed(data)
         if dctx is None:
+            pos, et = data["dd_edge_index"], data["dd_edge_type"]
             neg = data["neg_edge_index"] if neg_edge_index is None else neg_edge_index
-            pos_score, neg_score = self.dmt.score_pair(z, data["dd_edge_index"], neg, data["dd_edge_type"])
+            n_dec = self.gd.n_target
+        else:
+            pos, et = data["dd_edge_index_local"], data["dd_edge_type_local"]
+            neg = data["neg_edge_index_local"] if neg_edge_index is None else neg_edge_index
+            n_dec = dctx.world * dctx.block(data["n_d_global"])
+        # the decoder backward's (node, relation) structures depend on the edge lists only — the negatives' one is
+        # rebuilt every step (GripNet-pose.py:131 resamples them): start it NOW on a side stream, so the whole
+        # embedding pass hides it instead of the decoder waiting for it
+        prep = streams.Branch()
+        if torch.is_grad_enabled():
+            with prep(pos, neg, et):
+                G.pair_struct(neg, et, n_dec, self.dmt.num_et)
+                G.pair_struct(pos, et, n_dec, self.dmt.num_et)
+        z = self.embed(data)
+        prep.join()
+        if dctx is None:
+            pos_score, neg_score = self.dmt.score_pair(z, pos, neg, et)
             return link_prediction_loss(pos_score, neg_score), z, pos_score, neg_score
-        neg = data["neg_edge_index_local"] if neg_edge_index is None else neg_edge_index
         z_full = parallel.all_gather_rows(z, dctx, data["n_d_global"])
-        pos_score, neg_score = self.dmt.score_pair(z_full, data["dd_edge_index_local"], neg,
-                                                   data["dd_edge_type_local"])
+        pos_score, neg_score = self.dmt.score_pair(z_full, pos, neg, et)
         loss = parallel.global_mean_loss(link_prediction_loss(pos_score, neg_score), pos_score.numel(),
                                          data["e_dd_global"], dctx)
         return loss, z, pos_score, neg_score

@@ -194,23 +194,6 @@ int gn_spmm(const gn_csr* csr, const float* x, int64_t ldx, int32_t F,
             const float* row_scale, const float* bias, const float* addend, int64_t ld_addend,
             int relu, float* out, int64_t ldo, float* partial, void* stream);
 
-/* gn_spmm with a fused ROW TRANSFORM in its epilogue: while the finished output row h = out[i, 0:F] is still in
- * registers the warp also writes
- *   y2[i, 0:n2] = h . op(W) (+ addend2[i]) (zeroed where relu_mask2[i] <= 0),
- *   op(W)[k][j] = W[k*ldw + j] (transW == 0)  or  W[j*ldw + k] (transW != 0).
- * Forward: the NEXT layer's dense transform Y_{l+1} = H_l W_{l+1} (gripnet/layers.py:73 of the next conv);
- * backward: the previous layer's gradient dH_{l-1} = dY_l W_l^T + concat-slice gradient, ReLU-masked
- * (autograd of layers.py:73 and :279).  Removes one GEMM launch per layer from the step's dependency chain and an
- * [N, F] round trip; available when gn_spmm_fused_ok(F, n2) (F % 4 == 0, F <= 128, n2 <= 64, F*n2 <= 1024:
- * the narrow layers of the pose family) and the 128-bit alignment rules of gn_spmm hold. */
-int gn_spmm_fused_ok(int32_t F, int32_t n2);
-int gn_spmm_fused(const gn_csr* csr, const float* x, int64_t ldx, int32_t F,
-                  const float* row_scale, const float* bias, const float* addend, int64_t ld_addend,
-                  int relu, float* out, int64_t ldo, float* partial,
-                  const float* W, int32_t n2, int64_t ldw, int transW, float* y2, int64_t ldy2,
-                  const float* addend2, int64_t ld_addend2, const float* relu_mask2, int64_t ld_mask2,
-                  void* stream);
-
 /* ---- K2/K6: dense transforms (fp32 FFMA, CUDA cores)  --------------------- */
 /* C[b] = epilogue( alpha * op(A[b]) * op(B[b]) ), b in [0,batch):
  *   op(A) is M x K (transA: stored K x M), op(B) is K x N (transB: stored N x K);
@@ -230,15 +213,6 @@ int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
              float alpha, int accumulate, const float* addend, int64_t ld_addend,
              const float* relu_mask, int64_t ld_mask, const int64_t* a_rows,
              int32_t split_k, float* ws, size_t ws_bytes, void* stream);
-
-/* Tall-skinny TN product for the weight gradients of the narrow layers: C[K, F] = A^T B with A [n, K], B [n, F],
- * n = number of nodes (dW = H_{l-1}^T dY, autograd of gripnet/layers.py:73).  One launch: per-CTA partial
- * products over row slabs, summed in CTA order by the last CTA to arrive (deterministic).  Available when
- * gn_tn_gemm_ok(K, F) (K * F <= 2048); `ws` holds gn_tn_gemm_workspace_bytes(n, K, F) bytes, 16-byte aligned. */
-int gn_tn_gemm_ok(int32_t K, int32_t F);
-size_t gn_tn_gemm_workspace_bytes(int64_t n, int32_t K, int32_t F);
-int gn_tn_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t K, int32_t F,
-               float* C, int64_t ldc, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- K2/K6 tensor path: tcgen05 (kind::tf32) with 3xTF32 error compensation -- */
 /* C = epilogue( A[M,K] * op(B) ),  op(B) = B [K,N] (transB == 0) or B^T with B stored [N,K].
@@ -411,11 +385,14 @@ int gn_nc_metrics(const int64_t* target, const int64_t* pred, int64_t n, int32_t
 
 /* ---- K12: slot all-gather over NVLink peer memory (multi-GPU exchange step) ------------------ */
 /* New design (the reference is single-device).  Every rank of the node maps one
- * symmetric arena of identical layout; `arena_base` (HOST array, `world` entries) holds every rank's
- * arena base as this process sees it (peer-mapped device pointers).  The gather buffer is
+ * symmetric arena of identical layout; `arena_base` (HOST array, `world + 1` entries) holds every rank's
+ * arena base as this process sees it (peer-mapped device pointers) and, last, the MULTICAST (NVLS) mapping of
+ * the arena or 0: with it a slot leaves the GPU once (multimem.st) and the NVSwitch delivers it to every rank,
+ * instead of world-1 unicast copies.  The gather buffer is
  * [world][slot_bytes] at `buf_offset` of every arena; this rank's slot is already written.  The call
  * pushes the slot to every peer (128-bit P2P stores), publishes flag (flag_index, rank) = use counter
- * in every peer's flag block (u64 [n_buffers][gn_peer_max_world()] at `flag_offset`, zero-initialised)
+ * in every peer's flag block (u64 [n_buffers][gn_peer_max_world()] at `flag_offset`, zero-initialised;
+ * a flag counts the CTAs of its rank that have delivered, over all uses of the buffer)
  * and waits until all peers have published theirs: kernels enqueued after it on `stream` see the
  * complete buffer.  `seq` / `done`: this buffer's LOCAL use counter (u64) and CTA arrival counter
  * (u32), zero-initialised, owned by the caller; `abort_flag` (u32, zero-initialised, shared by all

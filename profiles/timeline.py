@@ -80,12 +80,14 @@ def main():
         ks.append((s0, s0 + float(e.get("dur", 0.0)), e.get("name", "?"), e.get("args", {}).get("stream", -1),
                    "kernel" if cat == "kernel" else "mem"))
     ks.sort()
-    # split into replays: the flush (a big memset / fill kernel) precedes each replay -> cut at gaps > 200 us
+    # split into replays at the L2 flush (the 252 MiB fill that precedes every replay)
     groups, cur = [], []
     for k in ks:
-        if cur and k[0] - max(x[1] for x in cur) > 150:
-            groups.append(cur)
+        if "FillFunctor<unsigned char>" in k[2] and k[1] - k[0] > 20:
+            if cur:
+                groups.append(cur)
             cur = []
+            continue
         cur.append(k)
     if cur:
         groups.append(cur)
@@ -129,8 +131,15 @@ def main():
     for name, (n, t) in sorted(per.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"{name[:60]:60s} {n:4d} {t:10.1f} {t / span:14.3f}")
     open(os.path.join(out_dir, f"{args.tag}_rank{rank}_summary.txt"), "w").write("\n".join(lines) + "\n")
+    # the step in launch order: start, duration, stream, kernel (the critical path is read off this list)
+    lines.append("")
+    lines.append("timeline (us from the first kernel of the step): start  dur  end  stream  kernel")
+    for s0, e0, name, stream, _ in g:
+        short = name.replace("void ", "").replace("gn::", "").split("(")[0][:70]
+        lines.append(f"{s0 - t0:9.1f} {e0 - s0:8.1f} {e0 - t0:9.1f}  st{stream}  {short}")
+    open(os.path.join(out_dir, f"{args.tag}_rank{rank}_summary.txt"), "w").write("\n".join(lines) + "\n")
     if rank == 0:
-        print("\n".join(lines[:40]))
+        print("\n".join(lines[:36]))
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
