@@ -457,8 +457,13 @@ using namespace gn;
 static int tc_set_smem_attr() {
   static std::atomic<int> attr_set{0};
   if (!attr_set.load(std::memory_order_acquire)) {
-    const cudaError_t e =
+    cudaError_t e =
         cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    // the products are HBM-bound streams of A: two CTAs per SM (smem <= 99 KB and <= 256 TMEM columns each for the
+    // layer transforms) double the loads in flight, so ask for the largest shared-memory carveout
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
       g_last_cuda_error.store(int(e), std::memory_order_relaxed);
