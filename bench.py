@@ -799,7 +799,8 @@ def run_cuda(args):
     if dctx is not None:
         exchange = {"peer_gathers": dctx.peer_gathers, "nccl_gathers": dctx.nccl_gathers,
                     "peer_reductions": dctx.peer_reductions, "nccl_reductions": dctx.nccl_reductions,
-                    "arena": dctx.arena is not None}
+                    "arena": dctx.arena is not None,
+                    "nvls_multicast": bool(dctx.arena is not None and dctx.arena.multicast)}
 
     # ---- BASELINE config 5 at this N (default pose run only): free the headline workload first
     config5 = None

@@ -258,59 +258,120 @@ __global__ void __launch_bounds__(256) pair_walk_kernel(const gn_csr csr, const 
   finish_row<LPE, VEC, NV>(csr, ci, acc, D, partial, emit);
 }
 
-// dz / dw from T (and an optional second T of another edge list).  One CTA per output row: blocks
-// [0, n_rel) form dw[r] = 1/2 sum_n z[n] .* T[n,r], blocks [n_rel, n_rel + n_nodes) form
-// dz[n] = sum_r T[n,r] .* w[r].  The CTA's threads are G groups of D columns; group g adds the terms
-// i = g, g + G, ... in order, then the G partial rows are added in group order: a fixed summation order.
+// dz / dw from T (and an optional second T of another edge list).
+//   dz[n] = sum_r T[n,r] .* w[r]          one CTA per node: its threads are G groups of D columns, group g adds the
+//                                          relations g, g + G, ... in order, then the G partial rows in group order;
+//   dw[r] = 1/2 sum_n z[n] .* T[n,r]      the long reduction (n_nodes terms per relation, strided rows of T): every
+//                                          relation is cut into n_slabs slabs of nodes, one CTA each, whose partial
+//                                          rows go to `ws`; the LAST slab of a relation to arrive (integer counter)
+//                                          adds the slabs in slab order.
+// Fixed summation orders everywhere: bit-reproducible.  dw CTAs take the first blocks so the long ones start first.
 constexpr int kGradThreads = 1024;
+constexpr int kGradSlabNodes = 96;     // nodes per dw slab: 8 rounds of 12 groups at D = 80
+
+__device__ __forceinline__ float grads_reduce_groups(float acc, int g, int G, int f, int D, float* red) {
+  if (g < G && f < D) red[g * D + f] = acc;
+  __syncthreads();
+  float s = 0.f;
+  if (g == 0 && f < D) {
+    s = red[f];
+    for (int k = 1; k < G; ++k) s += red[k * D + f];
+  }
+  __syncthreads();
+  return s;
+}
+
 __global__ void __launch_bounds__(kGradThreads) distmult_grads_kernel(const float* __restrict__ T,
                                                                      const float* __restrict__ T2, int n_nodes,
                                                                      int n_rel, int D, const float* __restrict__ z,
                                                                      int64_t ldz, const float* __restrict__ w,
                                                                      float* __restrict__ dz, int64_t lddz,
-                                                                     float* __restrict__ dw) {
+                                                                     float* __restrict__ dw, int n_slabs,
+                                                                     float* __restrict__ slab_part,
+                                                                     unsigned int* __restrict__ slab_count) {
   extern __shared__ float red[];                       // [G][D]
-  const int G = kGradThreads / D > 0 ? kGradThreads / D : 1;
-  // the dw rows (n_nodes terms each) are the long ones: they take the FIRST blocks so they start first
-  const bool is_dz = int(blockIdx.x) >= n_rel;
-  const int row = is_dz ? int(blockIdx.x) - n_rel : int(blockIdx.x);
-  const int n_terms = is_dz ? n_rel : n_nodes;
-  if (is_dz ? dz == nullptr : dw == nullptr) return;
-  for (int f0 = 0; f0 < D; f0 += kGradThreads) {       // D > 1024: column panels (G == 1)
-    const int g = D <= kGradThreads ? int(threadIdx.x) / D : 0;
-    const int f = D <= kGradThreads ? int(threadIdx.x) % D : f0 + int(threadIdx.x);
+  __shared__ int s_last;
+  const int G = kGradThreads / D;
+  const int g = int(threadIdx.x) / D, f = int(threadIdx.x) % D;
+  const int n_dw_blocks = dw ? n_rel * n_slabs : 0;
+  constexpr int kU = 8;
+  if (int(blockIdx.x) >= n_dw_blocks) {
+    // ---------------------------------------------------------------- dz row
+    const int row = int(blockIdx.x) - n_dw_blocks;
+    if (dz == nullptr || row >= n_nodes) return;
     float acc = 0.f;
-    if (g < G && f < D) {
-      // kU terms per round: every load of the round is issued before the first add (the terms are L2 / HBM
-      // round trips), the adds stay in term order
-      constexpr int kU = 8;
-      for (int i0 = g; i0 < n_terms; i0 += kU * G) {
+    if (g < G) {
+      for (int i0 = g; i0 < n_rel; i0 += kU * G) {
         float tv[kU], ov[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
           const int i = i0 + u * G;
           tv[u] = ov[u] = 0.f;
-          if (i < n_terms) {
-            const int64_t t = is_dz ? (int64_t(row) * n_rel + i) * D + f : (int64_t(i) * n_rel + row) * D + f;
+          if (i < n_rel) {
+            const int64_t t = (int64_t(row) * n_rel + i) * D + f;
             tv[u] = __ldg(T + t);
             if (T2) tv[u] += __ldg(T2 + t);
-            ov[u] = is_dz ? __ldg(w + int64_t(i) * D + f) : __ldg(z + int64_t(i) * ldz + f);
+            ov[u] = __ldg(w + int64_t(i) * D + f);
           }
         }
 #pragma unroll
         for (int u = 0; u < kU; ++u) acc = fmaf(tv[u], ov[u], acc);
       }
-      red[g * D + (f - f0)] = acc;
     }
-    __syncthreads();
-    if (g == 0 && f < D) {
-      float s = red[f - f0];
-      for (int k = 1; k < G; ++k) s += red[k * D + (f - f0)];
-      if (is_dz) dz[int64_t(row) * lddz + f] = s;
-      else dw[int64_t(row) * D + f] = 0.5f * s;
-    }
-    __syncthreads();
+    const float s = grads_reduce_groups(acc, g, G, f, D, red);
+    if (g == 0) dz[int64_t(row) * lddz + f] = s;
+    return;
   }
+  // ------------------------------------------------------------------ dw slab
+  const int rel = int(blockIdx.x) / n_slabs, slab = int(blockIdx.x) % n_slabs;
+  const int n0 = slab * kGradSlabNodes;
+  const int n1 = n0 + kGradSlabNodes < n_nodes ? n0 + kGradSlabNodes : n_nodes;
+  float acc = 0.f;
+  if (g < G) {
+    for (int i0 = n0 + g; i0 < n1; i0 += kU * G) {
+      float tv[kU], ov[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * G;
+        tv[u] = ov[u] = 0.f;
+        if (i < n1) {
+          const int64_t t = (int64_t(i) * n_rel + rel) * D + f;
+          tv[u] = __ldg(T + t);
+          if (T2) tv[u] += __ldg(T2 + t);
+          ov[u] = __ldg(z + int64_t(i) * ldz + f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) acc = fmaf(tv[u], ov[u], acc);
+    }
+  }
+  const float s = grads_reduce_groups(acc, g, G, f, D, red);
+  if (n_slabs == 1) {
+    if (g == 0) dw[int64_t(rel) * D + f] = 0.5f * s;
+    return;
+  }
+  if (g == 0) slab_part[(int64_t(rel) * n_slabs + slab) * D + f] = s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(slab_count + rel, 1u) == unsigned(n_slabs - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (g == 0) {
+    const float* p = slab_part + int64_t(rel) * n_slabs * D + f;
+    float t = 0.f;
+    int k = 0;
+    for (; k + 7 < n_slabs; k += 8) {                 // eight slabs in flight, added in slab order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + int64_t(k + u) * D);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
+    for (; k < n_slabs; ++k) t += __ldcg(p + int64_t(k) * D);
+    dw[int64_t(rel) * D + f] = 0.5f * t;
+  }
+  if (threadIdx.x == 0) slab_count[rel] = 0;
 }
 
 __global__ void pair_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
@@ -572,13 +633,30 @@ int gn_distmult_bwd_pairs(const gn_csr* pair_csr, const int32_t* ent_other, cons
   return GN_ERR_ARG;
 }
 
+size_t gn_distmult_grads_workspace_bytes(int32_t n_nodes, int32_t n_rel, int32_t D) {
+  const size_t slabs = size_t(ceil_div(n_nodes > 0 ? n_nodes : 1, kGradSlabNodes));
+  return align_up(size_t(n_rel > 0 ? n_rel : 1) * 4) + size_t(n_rel > 0 ? n_rel : 1) * slabs * size_t(D > 0 ? D : 1) * 4 + 256;
+}
+
 int gn_distmult_grads(const float* T, const float* T2, int32_t n_nodes, int32_t n_rel, int32_t D, const float* z,
-                      int64_t ldz, const float* w, float* dz, int64_t lddz, float* dw, void* stream) {
-  if (n_nodes <= 0 || n_rel <= 0 || D <= 0 || !T || !z || !w || (!dz && !dw)) return GN_ERR_ARG;
-  const int G = kGradThreads / D > 0 ? kGradThreads / D : 1;
-  const size_t smem = size_t(G) * size_t(D < kGradThreads ? D : kGradThreads) * sizeof(float);
-  GN_LAUNCH(distmult_grads_kernel, (unsigned)(n_nodes + n_rel), kGradThreads, smem, as_stream(stream), T, T2, n_nodes,
-            n_rel, D, z, ldz, w, dz, lddz, dw);
+                      int64_t ldz, const float* w, float* dz, int64_t lddz, float* dw, void* ws, size_t ws_bytes,
+                      void* stream) {
+  if (n_nodes <= 0 || n_rel <= 0 || D <= 0 || D > kGradThreads || !T || !z || !w || (!dz && !dw)) return GN_ERR_ARG;
+  cudaStream_t st = as_stream(stream);
+  const int n_slabs = int(ceil_div(n_nodes, kGradSlabNodes));
+  unsigned int* count = nullptr;
+  float* part = nullptr;
+  if (dw && n_slabs > 1) {
+    if (!ws || ws_bytes < gn_distmult_grads_workspace_bytes(n_nodes, n_rel, D)) return GN_ERR_WORKSPACE;
+    count = static_cast<unsigned int*>(ws);
+    part = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(size_t(n_rel) * 4));
+    if (cudaMemsetAsync(count, 0, size_t(n_rel) * 4, st) != cudaSuccess) return GN_ERR_CUDA;
+  }
+  const int G = kGradThreads / D;
+  const size_t smem = size_t(G) * size_t(D) * sizeof(float);
+  const int64_t blocks = int64_t(dw ? n_rel * n_slabs : 0) + (dz ? n_nodes : 0);
+  GN_LAUNCH(distmult_grads_kernel, (unsigned)blocks, kGradThreads, smem, st, T, T2, n_nodes, n_rel, D, z, ldz, w, dz,
+            lddz, dw, n_slabs, part, count);
   return GN_OK;
 }
 

@@ -643,8 +643,10 @@ def _distmult_grads(t, t2, z, w, need_z, need_w):
     dz = torch.empty((n, d), dtype=torch.float32, device=z.device) if need_z else None
     dw = torch.empty_like(w) if need_w else None
     if need_z or need_w:
-        _lib.check(_lib.load().gn_distmult_grads(t.data_ptr(), _ptr(t2), n, r, d, z.data_ptr(), _ldz(z), w.data_ptr(),
-                                                 _ptr(dz), d, _ptr(dw), _stream()), "gn_distmult_grads")
+        lib = _lib.load()
+        ws = _ws(lib.gn_distmult_grads_workspace_bytes(n, r, d), z.device)
+        _lib.check(lib.gn_distmult_grads(t.data_ptr(), _ptr(t2), n, r, d, z.data_ptr(), _ldz(z), w.data_ptr(),
+                                         _ptr(dz), d, _ptr(dw), _ptr(ws), ws.numel(), _stream()), "gn_distmult_grads")
     return dz, dw
 
 
