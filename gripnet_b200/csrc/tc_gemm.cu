@@ -29,24 +29,10 @@
 //     (k-block major), and each k-block arrives with ONE bulk async copy;
 //   * 2-3 smem stages, full/empty mbarriers; tcgen05.commit releases a stage when the
 //     MMAs that read it have retired.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gn {
 namespace tc {
-
-constexpr int BM = 128;          // rows per CTA tile == UMMA M
-constexpr int BK = 32;           // floats per k-block (4 UMMA k-steps of 8)
-constexpr int CHUNKS = BK / 4;   // 16-byte k-chunks per k-block
-constexpr int kLoaderWarps = 8;
-constexpr int kLoaderThreads = kLoaderWarps * 32;
-constexpr int kThreads = (kLoaderWarps + 2) * 32;
-constexpr int kMaxNt = 256;
-
-// one "plane" = all rows of one 16-byte k-chunk, 16 B per row, plus 16 B of padding so that
-// the 8 chunks of one row land in 8 different 16-byte bank groups (conflict-free staging)
-__host__ __device__ constexpr int plane_bytes(int rows) { return rows * 16 + 16; }
-__host__ __device__ constexpr int part_bytes(int rows) { return CHUNKS * plane_bytes(rows); }
-__host__ __device__ constexpr int stage_bytes(int nt) { return 2 * part_bytes(BM) + 2 * part_bytes(nt); }
 
 struct Params {
   int M, N, K;
@@ -63,99 +49,6 @@ struct Params {
   int n_acc;             // TMEM accumulator PAIRS (hi*hi | cross terms); each covers kb_per_acc k-blocks
   int kb_per_acc;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-  hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-  lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
-}
-
-// ---- mbarrier / proxy / tcgen05 wrappers (PTX ISA 8.6+, sm_100a) ------------------------
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 B stored
-// contiguously (128 B); SBO = distance between 8-row groups, LBO = distance between the two
-// 16-byte k-chunks of one UMMA k-step.  Blackwell descriptor version = 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
-  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= uint64_t(1) << 46;
-  return d;
-}
-
-// instruction descriptor for kind::tf32: D = F32, A = B = TF32, both K-major
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ---------------------------------------------------------------------------------------
 // B image: hi/lo split of op(B), laid out exactly as one smem stage wants it

@@ -159,6 +159,30 @@ def rel_transform(x, w, y, r, k, f, device):
     sgemm(False, False, n, f, k, x.ptr, x.ld, w.data_ptr(), f, y.ptr, y.ld, device, batch=r, sa=0, sb=k * f, sc=f)
 
 
+# weight gradients C = A^T B (reduction over the node rows): tensor cores when the reduction is long enough to be a
+# stream of the operands (or covers all relations at once), the split-K FFMA kernel otherwise
+_TC_TN_MIN_ROWS = 1 << 15
+
+
+def weight_grad(a, b, out, device, c_inner=0, c_stride=0, force_tc=False):
+    """``out = a^T b`` — ``a``: M [n, Mo], ``b``: M [n, No]; ``out``: contiguous [Mo, No] tensor, or with
+    ``c_inner`` the ``[No / c_inner][Mo][c_inner]`` relational layout.  Returns False when the tensor path does
+    not apply (the caller then runs its FFMA product)."""
+    lib = _lib.load()
+    n, mo, no = a.n, a.f, b.f
+    ok = GEMM_PATH != "ffma" and n > 0 and mo % 4 == 0 and no % 4 == 0 and a.ld % 4 == 0 and b.ld % 4 == 0 and \
+        a.ptr % 16 == 0 and b.ptr % 16 == 0 and (force_tc or GEMM_PATH == "tc" or n >= _TC_TN_MIN_ROWS)
+    if not ok:
+        return False
+    nbytes = int(lib.gn_tc_tn_workspace_bytes(n, mo, no))
+    if not nbytes:
+        return False
+    ws = _ws(nbytes, device)
+    _lib.check(lib.gn_tc_tn(a.ptr, a.ld, b.ptr, b.ld, n, mo, no, out.data_ptr(), no, int(c_inner), int(c_stride),
+                            _ptr(ws), nbytes, _stream()), "gn_tc_tn")
+    return True
+
+
 def map2d(op, src, dst):
     _lib.check(_lib.load().gn_map2d(op, src.ptr, src.ld, dst.ptr, dst.ld, src.n, src.f, _stream()), "gn_map2d")
 
@@ -286,8 +310,9 @@ class GcnStack(torch.autograd.Function):
                 dw = torch.empty((k, f), dtype=torch.float32, device=dev)
                 # dW = H_{l-1}^T dY : reduction over the node dimension -> deterministic split-K
                 with br(dy.t, h_prev.t):
-                    sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(), f,
-                          dev)
+                    if not weight_grad(h_prev, dy, dw, dev):
+                        sgemm(True, False, k, f, graph.n_src, h_prev.ptr, h_prev.ld, dy.ptr, dy.ld, dw.data_ptr(),
+                              f, dev)
                 grads[2 * (l - 1)] = _reduce(dctx, dw)
             need_prev = (l > 1) or ctx.needs_input_grad[0]
             dz_slot = None
@@ -456,8 +481,11 @@ class RgcnStack(torch.autograd.Function):
                 datt = torch.empty((r, nb), dtype=torch.float32, device=dev) if ctx.needs_input_grad[base + 1] else None
                 dbasis = torch.empty((nb, k, f), dtype=torch.float32, device=dev) if ctx.needs_input_grad[base] else None
                 with br(dy, h_prev.t, dw, bs, at):
-                    sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dy.data_ptr(), r * f, dw.data_ptr(), f, dev,
-                          batch=r, sa=0, sb=f, sc=k * f)
+                    # dW[r] = X^T dY[:, r, :] for all relations at once: one TN product on the tensor cores
+                    if not weight_grad(h_prev, M(dy.view(n, r * f)), dw, dev, c_inner=f, c_stride=k * f,
+                                       force_tc=True):
+                        sgemm(True, False, k, f, n, h_prev.ptr, h_prev.ld, dy.data_ptr(), r * f, dw.data_ptr(), f,
+                              dev, batch=r, sa=0, sb=f, sc=k * f)
                     if datt is not None:
                         sgemm(False, True, r, nb, k * f, dw.data_ptr(), k * f, bs.data_ptr(), k * f, datt.data_ptr(),
                               nb, dev)

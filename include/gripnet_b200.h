@@ -238,6 +238,17 @@ size_t gn_tc_gemm_rel_workspace_bytes(int32_t M, int32_t n_rel, int32_t f, int32
 int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
                    const float* W, float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
 
+/* Weight-gradient products on the tensor cores: C[Mo, No] = A^T B with A [n, Mo], B [n, No] (features contiguous,
+ * the reduction runs over the n node rows): dW = H_{l-1}^T dY of a GCN layer (autograd of gripnet/layers.py:73)
+ * and, with c_inner = f and c_stride = k*f, dW[r] = X^T dY[:, r, :] for every relation at once, written in the
+ * [R][k][f] layout of the relational weights (layers.py:171-189).  3xTF32 with fp32 running sums in registers
+ * (the TMEM accumulator is drained every 128 rows); rows are split over CTAs and the split partials are added in
+ * split order.  c_inner == 0: C row-major with leading dimension ldc.  Requirements: A / B 16-byte aligned, lda,
+ * ldb, Mo, No multiples of 4; `ws` holds gn_tc_tn_workspace_bytes(n, Mo, No) bytes. */
+size_t gn_tc_tn_workspace_bytes(int64_t n, int32_t Mo, int32_t No);
+int gn_tc_tn(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t n, int32_t Mo, int32_t No,
+             float* C, int64_t ldc, int32_t c_inner, int64_t c_stride, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K9/K10: DistMult decoder  ------------------------------------------- */
 /* score_e = sum_k z[src_e,k] z[dst_e,k] w[rel_e,k]; sigmoid optional.
  * Replaces gripnet/decoder.py:19-23 (three [E,D] gathers + two muls + sum). */

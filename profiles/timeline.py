@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--workload", default="pose")
     ap.add_argument("--tag", default="timeline")
     ap.add_argument("--replays", type=int, default=4)
+    ap.add_argument("--no-flush", action="store_true", help="replay with a warm L2 (a 1-byte fill marks the replays)")
     args = ap.parse_args()
     import bench
     import torch.distributed as dist
@@ -57,7 +58,7 @@ def main():
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(args.replays):
-            flush.zero_()
+            (flush[:1] if args.no_flush else flush).zero_()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -83,7 +84,7 @@ def main():
     # split into replays at the L2 flush (the 252 MiB fill that precedes every replay)
     groups, cur = [], []
     for k in ks:
-        if "FillFunctor<unsigned char>" in k[2] and k[1] - k[0] > 20:
+        if "FillFunctor<unsigned char>" in k[2] and (args.no_flush or k[1] - k[0] > 20):
             if cur:
                 groups.append(cur)
             cur = []

@@ -104,3 +104,52 @@ def test_dispatch_routes_tall_products_to_tensor_cores():
     ops.sgemm(False, False, m, n2, k, A.data_ptr(), k, W2.data_ptr(), n2, C2.data_ptr(), n2, d)
     assert gb.launch_count() - before == 2
     assert rel_err(C2, A.double() @ W2.double()) < 2e-6
+
+
+@pytest.mark.parametrize("n,mo,no,inner", [(645, 48, 512, 32), (645, 48, 35104, 32), (5000, 32, 16, 0), (70000, 64, 64, 0),
+                                           (200000, 192, 64, 0), (33, 4, 8, 0), (4097, 128, 128, 0),
+                                           (1000, 256, 32, 0)])
+def test_tc_tn_weight_gradient_products(n, mo, no, inner):
+    """C = A^T B on tcgen05 (gn_tc_tn: transposing 3xTF32 loaders, TMEM runs drained into fp32 registers, split
+    partials added in order) against float64 — GCN dW shapes, long reductions over several splits, and the
+    relation-batched dW of config 4 written in the [R][k][f] layout.  1e-5 relative like every fp32 result."""
+    from gripnet_b200 import ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(n + mo + no)
+    a = torch.randn(n, mo, generator=gen)
+    b = torch.randn(n, no, generator=gen)
+    big = torch.zeros(n, mo + 8)
+    big[:, 4:4 + mo] = a
+    ad = big.to(d)[:, 4:4 + mo]                                   # a column slice: leading dimension != width
+    bd = b.to(d)
+    ref = a.double().t() @ b.double()
+    outs = []
+    for _ in range(2):
+        if inner:
+            out = torch.empty(no // inner, mo, inner, device=d)
+            ok = ops.weight_grad(ops.M(ad), ops.M(bd), out, d, c_inner=inner, c_stride=mo * inner, force_tc=True)
+        else:
+            out = torch.empty(mo, no, device=d)
+            ok = ops.weight_grad(ops.M(ad), ops.M(bd), out, d, force_tc=True)
+        assert ok, "the tensor path must accept these aligned shapes"
+        outs.append(out)
+    torch.cuda.synchronize()
+    got = outs[0].permute(1, 0, 2).reshape(mo, no) if inner else outs[0]
+    err = float((got.double().cpu() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err
+    assert torch.equal(outs[0], outs[1])                          # deterministic
+
+
+@pytest.mark.parametrize("n,k,r,f", [(645, 48, 16, 32), (645, 48, 1097, 32), (130, 16, 3, 8), (5000, 64, 40, 16)])
+def test_tc_relation_batched_transform(n, k, r, f):
+    """Y[:, r, :] = X W[r] for every relation at once on tcgen05 (gn_tc_gemm_rel, W kept in its [R][k][f] layout)."""
+    from gripnet_b200 import ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(n + r)
+    x = torch.randn(n, k, generator=gen)
+    w = torch.randn(r, k, f, generator=gen) / np.sqrt(k)
+    xd, wd = x.to(d), w.to(d)
+    y = torch.empty(n, r * f, device=d)
+    ops.rel_transform(ops.M(xd), wd, ops.M(y), r, k, f, d)
+    ref = torch.einsum("nk,rkf->nrf", x.double(), w.double()).reshape(n, r * f)
+    assert rel_err(y, ref) < 1e-5
