@@ -66,8 +66,6 @@ SIGNATURES = {
     "gn_gcn_part_values": (_INT, [_P, _P, _I32, _I32, _P, _P, _INT, _P, _P]),
     "gn_rgcn_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "gn_rgcn_prep": (_INT, [_P, _P, _I64, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "gn_edge_prep_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
-    "gn_edge_prep": (_INT, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gn_index_prep_workspace_bytes": (_SZ, [_I64, _I32]),
     "gn_index_prep": (_INT, [_P, _I64, _I32, _P, _P, _P, _SZ, _P]),
     "gn_spmm": (_INT, [_CSR, _P, _I64, _I32, _P, _P, _P, _I64, _INT, _P, _I64, _P, _P]),
@@ -82,8 +80,6 @@ SIGNATURES = {
     "gn_tc_tn": (_INT, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _I32, _I64, _P, _SZ, _P]),
     "gn_distmult_fwd": (_INT, [_P, _I64, _I32, _P, _P, _P, _P, _I64, _INT, _P, _P]),
     "gn_distmult_coef": (_INT, [_P, _P, _I64, _INT, _P, _P]),
-    "gn_distmult_bwd_z": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _I64, _P, _P]),
-    "gn_distmult_bwd_w": (_INT, [_CSR, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),
     "gn_pair_prep_workspace_bytes": (_SZ, [_I64]),
     "gn_pair_prep": (_INT, [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P, _SZ, _P]),
     "gn_distmult_bwd_pairs": (_INT, [_CSR, _P, _P, _P, _P, _I64, _I32, _P, _P, _P]),

@@ -57,146 +57,6 @@ __global__ void distmult_coef_kernel(const float* __restrict__ grad_out, const f
 }
 
 // ---------------------------------------------------------------------------
-// backward: row-split segmented reductions (no atomics on data)
-//   MODE 0: rows = nodes,     entry (other, rel, e): coef[e] * z[other] .* w[rel]
-//   MODE 1: rows = relations, entry e:               coef[e] * z[src_e] .* z[dst_e]
-// MODE 0 keeps a per-relation run accumulator t = sum coef * z[other] and multiplies by
-// w[rel] only when the relation changes: edge lists are relation-major in practice
-// (GripNet-pose.py:54-56), a stable sort by node keeps that order inside every row, so
-// the w gather and half of the FMAs drop out.  Any order stays correct.
-// Two entries per slot are in flight per iteration (indices first, then the row gathers).
-// ---------------------------------------------------------------------------
-template <int LPE, int VEC, int NV, int MODE>
-__global__ void __launch_bounds__(256) distmult_bwd_kernel(const gn_csr csr, const int32_t* __restrict__ ent_a,
-                                                           const int32_t* __restrict__ ent_b,
-                                                           const int32_t* __restrict__ ent_eid,
-                                                           const int64_t* __restrict__ src,
-                                                           const int64_t* __restrict__ dst,
-                                                           const float* __restrict__ coef, const float* __restrict__ z,
-                                                           int64_t ldz, int D, const float* __restrict__ w,
-                                                           float* __restrict__ outp, int64_t ldo,
-                                                           float* __restrict__ partial) {
-  ChunkInfo ci;
-  if (!chunk_info(csr, ci)) return;
-  constexpr int EPI = 32 / LPE;
-  const int lane = threadIdx.x & 31;
-  const int slot = lane / LPE, fl = lane % LPE;
-
-  Vec<VEC> acc[NV], run[NV];
-#pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[v].v[i] = run[v].v[i] = 0.f;
-  int cur_rel = -1;
-
-  auto flush = [&](int rel) {
-    const float* wr = w + int64_t(rel) * D;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int f = (v * LPE + fl) * VEC;
-      if (f < D) {
-        const Vec<VEC> b = load_vec<VEC>(wr + f);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          acc[v].v[i] = fmaf(run[v].v[i], b.v[i], acc[v].v[i]);
-          run[v].v[i] = 0.f;
-        }
-      }
-    }
-  };
-
-  for (int s0 = ci.beg + slot; s0 < ci.end; s0 += 2 * EPI) {
-    const int s1 = s0 + EPI;
-    const bool has1 = s1 < ci.end;
-    // ---- indices of both entries
-    // ent_eid == nullptr: entry s IS edge s (a relation-major edge list walked by its relation CSR)
-    const int e0 = ent_eid ? __ldg(ent_eid + s0) : s0;
-    const int e1 = has1 ? (ent_eid ? __ldg(ent_eid + s1) : s1) : 0;
-    const float* pa0;
-    const float* pa1 = z;
-    const float* pb0 = z;
-    const float* pb1 = z;
-    int rel0 = 0, rel1 = 0;
-    if (MODE == 0) {
-      pa0 = z + int64_t(__ldg(ent_a + s0)) * ldz;
-      rel0 = __ldg(ent_b + s0);
-      if (has1) {
-        pa1 = z + int64_t(__ldg(ent_a + s1)) * ldz;
-        rel1 = __ldg(ent_b + s1);
-      }
-    } else {
-      pa0 = z + src[e0] * ldz;
-      pb0 = z + dst[e0] * ldz;
-      if (has1) {
-        pa1 = z + src[e1] * ldz;
-        pb1 = z + dst[e1] * ldz;
-      }
-    }
-    const float g0 = __ldg(coef + e0);
-    const float g1 = has1 ? __ldg(coef + e1) : 0.f;
-    if (MODE == 0) {
-      // ---- gathers of both rows, then the run logic in entry order
-      Vec<VEC> a0[NV], a1[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int f = (v * LPE + fl) * VEC;
-        if (f < D) {
-          a0[v] = load_vec<VEC>(pa0 + f);
-          a1[v] = load_vec<VEC>(pa1 + f);
-        }
-      }
-      if (rel0 != cur_rel) {
-        if (cur_rel >= 0) flush(cur_rel);
-        cur_rel = rel0;
-      }
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int f = (v * LPE + fl) * VEC;
-        if (f < D) {
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) run[v].v[i] = fmaf(g0, a0[v].v[i], run[v].v[i]);
-        }
-      }
-      if (has1) {
-        if (rel1 != cur_rel) {
-          flush(cur_rel);
-          cur_rel = rel1;
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int f = (v * LPE + fl) * VEC;
-          if (f < D) {
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) run[v].v[i] = fmaf(g1, a1[v].v[i], run[v].v[i]);
-          }
-        }
-      }
-    } else {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int f = (v * LPE + fl) * VEC;
-        if (f < D) {
-          const Vec<VEC> a0 = load_vec<VEC>(pa0 + f), b0 = load_vec<VEC>(pb0 + f);
-          const Vec<VEC> a1 = load_vec<VEC>(pa1 + f), b1 = load_vec<VEC>(pb1 + f);
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) {
-            acc[v].v[i] = fmaf(g0 * a0.v[i], b0.v[i], acc[v].v[i]);
-            acc[v].v[i] = fmaf(g1 * a1.v[i], b1.v[i], acc[v].v[i]);   // g1 == 0 when the slot has no 2nd entry
-          }
-        }
-      }
-    }
-  }
-  if (MODE == 0 && cur_rel >= 0) flush(cur_rel);
-#pragma unroll
-  for (int v = 0; v < NV; ++v) reduce_slots<LPE, VEC>(acc[v]);
-
-  const int row = ci.row;
-  auto emit = [&](int, int f, const Vec<VEC>& sum) { store_vec<VEC>(outp + int64_t(row) * ldo + f, sum); };
-  finish_row<LPE, VEC, NV>(csr, ci, acc, D, partial, emit);
-}
-
-// ---------------------------------------------------------------------------
 // backward in ONE gather pass (K10).  The endpoint entries of an edge list are grouped by (node, relation)
 // — the "pair CSR", rows = node * n_rel + rel — and one walk forms
 //     T[n, r, :] = sum over the entries (other, e) of pair row (n, r) of coef[e] * z[other, :].
@@ -451,45 +311,6 @@ inline WidthPlan plan_width(int D, bool can_vec4, bool wide = false) {
   return p;
 }
 
-template <int MODE>
-static int launch_bwd(const gn_csr& csr, const int32_t* ent_a, const int32_t* ent_b, const int32_t* ent_eid,
-                      const int64_t* src, const int64_t* dst, const float* coef, const float* z, int64_t ldz, int D,
-                      const float* w, float* outp, int64_t ldo, float* partial, cudaStream_t st) {
-  if (csr.n_rows == 0 || csr.n_chunks == 0) return GN_OK;
-  if (csr.n_chunks > csr.n_rows && !partial) return GN_ERR_ARG;
-  const bool v4 = (D % 4 == 0) && (ldz % 4 == 0) && (ldo % 4 == 0) && aligned16(z) && aligned16(outp) &&
-                  (!w || aligned16(w)) && (!partial || aligned16(partial));
-  // 8 lanes x 3 vectors per entry for the node-row (dz) walk: 80 registers instead of 128, three CTAs per SM
-  // instead of two (measured: 37.8 -> 35.5 us at pose-0 size; the relation-row (dw) walk is slower that way:
-  // 40.8 -> 52.7 us).  GRIPNET_B200_DECODER_LPE8 = "", "z", "w" or "zw" overrides the choice.
-  static const int wide_mode = [] {
-    const char* e = getenv("GRIPNET_B200_DECODER_LPE8");
-    if (!e) return 1;
-    int m = 0;
-    for (const char* c = e; *c; ++c) m |= (*c == 'z') ? 1 : (*c == 'w') ? 2 : 0;
-    return m;
-  }();
-  const WidthPlan p = plan_width(D, v4, (wide_mode & (MODE == 0 ? 1 : 2)) != 0);
-  if (!p.ok) return GN_ERR_ARG;
-  const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
-#define GN_BWD_CASE(L, V, N)                                                                                         \
-  if (p.lpe == L && p.vec == V && p.nv == N) {                                                                       \
-    GN_LAUNCH((distmult_bwd_kernel<L, V, N, MODE>), grid, 256, 0, st, csr, ent_a, ent_b, ent_eid, src, dst, coef, z, \
-              ldz, D, w, outp, ldo, partial);                                                                        \
-    return GN_OK;                                                                                                    \
-  }
-#define GN_BWD_CASES(L, V) GN_BWD_CASE(L, V, 1) GN_BWD_CASE(L, V, 2) GN_BWD_CASE(L, V, 4) GN_BWD_CASE(L, V, 5) \
-  GN_BWD_CASE(L, V, 8)
-  GN_BWD_CASES(4, 4)
-  GN_BWD_CASE(8, 4, 3)
-  GN_BWD_CASES(32, 4)
-  GN_BWD_CASES(4, 1)
-  GN_BWD_CASES(32, 1)
-#undef GN_BWD_CASES
-#undef GN_BWD_CASE
-  return GN_ERR_ARG;
-}
-
 }  // namespace gn
 
 using namespace gn;
@@ -533,24 +354,6 @@ int gn_distmult_coef(const float* grad_out, const float* out, int64_t n_edges, i
   GN_LAUNCH(distmult_coef_kernel, (unsigned)ceil_div(n_edges, 256), 256, 0, as_stream(stream), grad_out, out, n_edges,
             sigmoid, coef);
   return GN_OK;
-}
-
-int gn_distmult_bwd_z(const gn_csr* node_csr, const int32_t* ent_other, const int32_t* ent_rel,
-                      const int32_t* ent_eid, const float* coef, const float* z, int64_t ldz, int32_t D,
-                      const float* w, float* dz, int64_t lddz, float* partial, void* stream) {
-  if (!node_csr || !z || !w || !dz || D <= 0) return GN_ERR_ARG;
-  if (node_csr->nnz > 0 && (!ent_other || !ent_rel || !ent_eid || !coef)) return GN_ERR_ARG;
-  return launch_bwd<0>(*node_csr, ent_other, ent_rel, ent_eid, nullptr, nullptr, coef, z, ldz, D, w, dz, lddz,
-                       partial, as_stream(stream));
-}
-
-int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64_t* src, const int64_t* dst,
-                      const float* coef, const float* z, int64_t ldz, int32_t D, float* dw, float* partial,
-                      void* stream) {
-  if (!rel_csr || !z || !dw || D <= 0) return GN_ERR_ARG;
-  if (rel_csr->nnz > 0 && (!src || !dst || !coef)) return GN_ERR_ARG;      // rel_eid == NULL: identity order
-  return launch_bwd<1>(*rel_csr, nullptr, nullptr, rel_eid, src, dst, coef, z, ldz, D, nullptr, dw, D, partial,
-                       as_stream(stream));
 }
 
 int gn_softmax_fwd(const float* logits, int64_t n, int32_t C, float* out, void* stream) {

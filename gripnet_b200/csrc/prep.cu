@@ -221,31 +221,8 @@ __global__ void rgcn_bwd_fill_kernel(const int32_t* __restrict__ perm_t, const i
 }
 
 // ---------------------------------------------------------------------------
-// decoder prep
+// index-list prep
 // ---------------------------------------------------------------------------
-__global__ void edge_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
-                                 const int64_t* __restrict__ etype, int64_t n_edges, int32_t* __restrict__ node_key,
-                                 int32_t* __restrict__ rel_key) {
-  const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (e >= n_edges) return;
-  node_key[e] = int32_t(src[e]);
-  node_key[n_edges + e] = int32_t(dst[e]);
-  rel_key[e] = int32_t(etype[e]);
-}
-
-__global__ void edge_fill_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
-                                 const int64_t* __restrict__ etype, int64_t n_edges, const int32_t* __restrict__ perm,
-                                 int32_t* __restrict__ ent_other, int32_t* __restrict__ ent_rel,
-                                 int32_t* __restrict__ ent_eid) {
-  const int64_t s = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (s >= 2 * n_edges) return;
-  const int64_t q = perm[s];
-  const int64_t e = q < n_edges ? q : q - n_edges;
-  ent_other[s] = int32_t(q < n_edges ? dst[e] : src[e]);
-  ent_rel[s] = int32_t(etype[e]);
-  ent_eid[s] = int32_t(e);
-}
-
 __global__ void narrow_kernel(const int64_t* __restrict__ in, int64_t n, int32_t* __restrict__ out) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = int32_t(in[i]);
@@ -402,60 +379,6 @@ int gn_rgcn_prep(const int64_t* src, const int64_t* dst, int64_t n_edges, const 
   if (E > 0) {
     GN_LAUNCH(rgcn_bwd_fill_kernel, grid1d(E), 256, 0, st, (const int32_t*)perm_t, (const int32_t*)key_dst,
               (const float*)inv_cnt, E, col_t, val_t);
-  }
-  return GN_OK;
-}
-
-size_t gn_edge_prep_workspace_bytes(int64_t n_edges, int32_t n_nodes, int32_t n_rel) {
-  (void)n_nodes;
-  (void)n_rel;
-  const size_t E = size_t(n_edges > 0 ? n_edges : 1);
-  const size_t multi = 2 * align_up(2 * E * 4) + 3 * align_up(E * 4) + sort_ws_bytes(2 * n_edges) + 4096;
-  const size_t single = rs_single_pass_ws_bytes(2 * n_edges, 10) + 4096;
-  return multi > single ? multi : single;
-}
-
-int gn_edge_prep(const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges, int32_t n_nodes,
-                 int32_t n_rel, int32_t* node_rowptr, int32_t* ent_other, int32_t* ent_rel, int32_t* ent_eid,
-                 int32_t* rel_rowptr, int32_t* rel_eid, void* ws, size_t ws_bytes, void* stream) {
-  if (n_edges < 0 || n_nodes <= 0 || n_rel <= 0 || !node_rowptr) return GN_ERR_ARG;
-  if (n_edges > 0 && (!src || !dst || !etype || !ent_other || !ent_rel || !ent_eid)) return GN_ERR_ARG;
-  if (rel_rowptr && n_edges > 0 && !rel_eid) return GN_ERR_ARG;
-  if (2 * n_edges >= (int64_t(1) << 31)) return GN_ERR_RANGE;
-  cudaStream_t st = as_stream(stream);
-  const int64_t E = n_edges;
-  const int node_bits = bits_for(n_nodes > 1 ? n_nodes : 2);
-  if (node_bits <= 10) {
-    // small supervertex (the usual link-prediction case): ONE counting pass straight from the
-    // int64 endpoint arrays, entries written in place, row pointers from the scanned histogram
-    const EndpointKeys ks{src, dst, E};
-    const EndpointSink sink{src, dst, etype, E, ent_other, ent_rel, ent_eid};
-    if (node_bits <= 8) GN_CHECK((rs_single_pass<8>(ks, sink, 2 * E, node_rowptr, n_nodes, ws, ws_bytes, st)));
-    else GN_CHECK((rs_single_pass<10>(ks, sink, 2 * E, node_rowptr, n_nodes, ws, ws_bytes, st)));
-    if (rel_rowptr) GN_CHECK(gn_index_prep(etype, E, n_rel, rel_rowptr, rel_eid, ws, ws_bytes, stream));
-    return GN_OK;
-  }
-  const size_t Ea = size_t(E > 0 ? E : 1);
-  Arena a(ws, ws_bytes);
-  int32_t* node_key = a.take<int32_t>(2 * Ea);
-  int32_t* sorted = a.take<int32_t>(2 * Ea);
-  int32_t* rel_key = a.take<int32_t>(Ea);
-  int32_t* perm = a.take<int32_t>(2 * Ea);
-  if (!a.ok()) return GN_ERR_WORKSPACE;
-  void* sub_ws = a.base + a.off;
-  const size_t sub_bytes = a.cap - a.off;
-  if (E > 0) {
-    GN_LAUNCH(edge_keys_kernel, grid1d(E), 256, 0, st, src, dst, etype, E, node_key, rel_key);
-  }
-  GN_CHECK(sort_pairs(node_key, nullptr, sorted, perm, 2 * E, node_bits, sub_ws, sub_bytes, st));
-  GN_CHECK(rowptr_from_sorted(sorted, 2 * E, n_nodes, node_rowptr, st));
-  if (E > 0) {
-    GN_LAUNCH(edge_fill_kernel, grid1d(2 * E), 256, 0, st, src, dst, etype, E, (const int32_t*)perm, ent_other,
-              ent_rel, ent_eid);
-  }
-  if (rel_rowptr) {
-    GN_CHECK(sort_pairs(rel_key, nullptr, sorted, rel_eid, E, bits_for(n_rel > 1 ? n_rel : 2), sub_ws, sub_bytes, st));
-    GN_CHECK(rowptr_from_sorted(sorted, E, n_rel, rel_rowptr, st));
   }
   return GN_OK;
 }

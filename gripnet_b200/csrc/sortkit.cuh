@@ -28,14 +28,6 @@ struct LongKeys {
   __device__ __forceinline__ int key(int64_t i) const { return int(k[i]); }
 };
 
-// virtual key array of an edge list: [src_0..src_{E-1}, dst_0..dst_{E-1}]
-struct EndpointKeys {
-  const int64_t* src;
-  const int64_t* dst;
-  int64_t n_edges;
-  __device__ __forceinline__ int key(int64_t i) const { return int(i < n_edges ? src[i] : dst[i - n_edges]); }
-};
-
 struct PairSink {
   int32_t* keys_out;
   int32_t* vals_out;
@@ -50,24 +42,6 @@ struct PairSink {
 struct PermSink {
   int32_t* perm;
   __device__ __forceinline__ void put(int pos, int, int64_t idx) const { perm[pos] = int32_t(idx); }
-};
-
-// endpoint-CSR entry (other endpoint, relation, edge id) written in place
-struct EndpointSink {
-  const int64_t* src;
-  const int64_t* dst;
-  const int64_t* etype;
-  int64_t n_edges;
-  int32_t* ent_other;
-  int32_t* ent_rel;
-  int32_t* ent_eid;
-  __device__ __forceinline__ void put(int pos, int, int64_t idx) const {
-    const bool first = idx < n_edges;
-    const int64_t e = first ? idx : idx - n_edges;
-    ent_other[pos] = int32_t(first ? dst[e] : src[e]);
-    ent_rel[pos] = int32_t(etype[e]);
-    ent_eid[pos] = int32_t(e);
-  }
 };
 
 template <int RB, typename KeySrc>

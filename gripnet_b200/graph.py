@@ -413,36 +413,6 @@ class DistRgcnGraph:
         self.bwd = slice_csr(g.bwd, r0 * n_rel, r1 * n_rel, ctx.world * self.b)
 
 
-class EdgeStruct:
-    """Endpoint CSR of an edge list (deterministic DistMult backward w.r.t. z).
-
-    The relation CSR (backward w.r.t. the decoder weight) depends on ``edge_type`` only and is
-    cached separately (``rel_struct``), so positive and negative lists that share their types —
-    as in ``GripNet-pose.py:131-138`` — build it once.
-    """
-
-    def __init__(self, edge_index, edge_type, n_nodes, n_rel, exact):
-        lib = _lib.load()
-        dev = edge_index.device
-        E = int(edge_index.size(1))
-        if 2 * E >= 2 ** 31:
-            raise RuntimeError("gripnet_b200: 2*E must be < 2^31")
-        ei = edge_index.contiguous()
-        et = edge_type.contiguous()
-        self.edge_index, self.edge_type = ei, et
-        i32 = dict(dtype=torch.int32, device=dev)
-        node_rowptr = torch.empty(n_nodes + 1, **i32)
-        self.ent_other = torch.empty(max(2 * E, 1), **i32)
-        self.ent_rel = torch.empty(max(2 * E, 1), **i32)
-        self.ent_eid = torch.empty(max(2 * E, 1), **i32)
-        ws = _ws(lib.gn_edge_prep_workspace_bytes(E, n_nodes, n_rel), dev)
-        _lib.check(lib.gn_edge_prep(_ptr(ei[0]) if E else None, _ptr(ei[1]) if E else None, _ptr(et) if E else None,
-                                    E, n_nodes, n_rel, _ptr(node_rowptr), _ptr(self.ent_other), _ptr(self.ent_rel),
-                                    _ptr(self.ent_eid), None, None, _ptr(ws), ws.numel(),
-                                    _stream()), "gn_edge_prep")
-        self.node = Csr(node_rowptr, self.ent_other, None, n_nodes, n_nodes, 2 * E, exact=exact)
-
-
 class PairStruct:
     """(node, relation) pair CSR of an edge list — rows = ``node * n_rel + rel``, entries = (other endpoint,
     edge id) — for the one-gather-pass DistMult backward (``gn_pair_prep`` / ``gn_distmult_bwd_pairs``)."""
@@ -605,25 +575,11 @@ def rgcn_graph(edge_index, range_list, n_nodes, n_rel):
     return _cache.get(key, (edge_index, range_list), lambda: RgcnGraph(edge_index, range_list, n_nodes, n_rel))
 
 
-def edge_struct(edge_index, edge_type, n_nodes, n_rel):
-    key = ("edge", _Cache.tkey(edge_index), _Cache.tkey(edge_type), n_nodes, n_rel)
-    exact = not _capturing()
-    return _cache.get(key, (edge_index, edge_type),
-                      lambda: EdgeStruct(edge_index, edge_type, n_nodes, n_rel, exact))
-
-
 def pair_struct(edge_index, edge_type, n_nodes, n_rel):
     key = ("pair", _Cache.tkey(edge_index), _Cache.tkey(edge_type), n_nodes, n_rel)
     exact = not _capturing()
     return _cache.get(key, (edge_index, edge_type),
                       lambda: PairStruct(edge_index, edge_type, n_nodes, n_rel, exact))
-
-
-def rel_struct(edge_type, n_rel):
-    """Relation CSR of an edge-type list: row r lists the edge ids of relation r."""
-    key = ("rel", _Cache.tkey(edge_type), n_rel)
-    exact = not _capturing()
-    return _cache.get(key, (edge_type,), lambda: IndexStruct(edge_type, n_rel, exact))
 
 
 def index_struct(index, n_nodes):

@@ -227,8 +227,6 @@ class GcnStack(torch.autograd.Function):
             buf = _new(graph.n_dst, sum(dims), x0)
             offs = [sum(dims[:i]) for i in range(len(dims))]
             h0 = M(buf, offs[0], dims[0])
-            with br(x0):                         # the concat copy of H_0 is off the chain: layer 0 reads x0 itself
-                map2d(_lib.EW_COPY, M(x0), h0)
             outs.append(h0)
         else:
             buf = None
@@ -239,6 +237,9 @@ class GcnStack(torch.autograd.Function):
             y = Slot(graph.n_src, f, x0, dctx, b_src)
             xin = M(x0) if l == 0 else outs[l]
             sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, y.m.ld, dev)
+            if l == 0 and catout:
+                with br(x0):                     # the concat copy of H_0 is off the chain (layer 0 reads x0 itself);
+                    map2d(_lib.EW_COPY, M(x0), h0)   # forked behind the first transform: the chain starts first
             if catout:
                 hl = M(buf, offs[l + 1], f)
             else:

@@ -27,8 +27,10 @@ class PoseModel(Module):
         self.dd = homoGraph(dd, multi_relational=True, n_rela=n_rel, n_base=n_base)
         self.dmt = multiRelaInnerProductDecoder(sum(dd), n_rel)
 
-    def embed(self, data):
+    def embed(self, data, after_first=None):
         z = self.gg(None, data["gg_edge_index"], edge_weight=data.get("gg_edge_weight"), if_catout=True)
+        if after_first is not None:
+            after_first()
         z = self.gd(z, data["gd_edge_index"], mod="cat", if_relu=True)
         return self.dd(z, data["dd_edge_index"], edge_type=data["dd_edge_type"],
                        range_list=data["dd_range_list"], if_catout=True)
@@ -52,14 +54,18 @@ class PoseModel(Module):
             neg = data["neg_edge_index_local"] if neg_edge_index is None else neg_edge_index
             n_dec = dctx.world * dctx.block(data["n_d_global"])
         # the decoder backward's (node, relation) structures depend on the edge lists only — the negatives' one is
-        # rebuilt every step (GripNet-pose.py:131 resamples them): start it NOW on a side stream, so the whole
-        # embedding pass hides it instead of the decoder waiting for it
+        # rebuilt every step (GripNet-pose.py:131 resamples them): it runs on a side stream next to the embedding
+        # pass instead of the decoder waiting for it.  It is forked right AFTER the first supervertex has been
+        # enqueued: the step's dependency chain is then the first root of the captured graph and starts at once
         prep = streams.Branch()
-        if torch.is_grad_enabled():
-            with prep(pos, neg, et):
-                G.pair_struct(neg, et, n_dec, self.dmt.num_et)
-                G.pair_struct(pos, et, n_dec, self.dmt.num_et)
-        z = self.embed(data)
+
+        def fork_prep():
+            if torch.is_grad_enabled():
+                with prep(pos, neg, et):
+                    G.pair_struct(neg, et, n_dec, self.dmt.num_et)
+                    G.pair_struct(pos, et, n_dec, self.dmt.num_et)
+
+        z = self.embed(data, after_first=fork_prep)
         prep.join()
         if dctx is None:
             pos_score, neg_score = self.dmt.score_pair(z, pos, neg, et)

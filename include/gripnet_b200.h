@@ -163,18 +163,6 @@ int gn_rgcn_prep(const int64_t* src, const int64_t* dst, int64_t n_edges,
                  int32_t* rowptr_t /*[n_nodes*n_rel+1]*/, int32_t* col_t, float* val_t, int32_t* perm_t,
                  void* ws, size_t ws_bytes, void* stream);
 
-/* Endpoint CSR of an edge list for the deterministic DistMult backward:
- * rows = nodes, 2E entries; entry = (other endpoint, relation, edge id).
- * Also the relation CSR (rows = relations, E entries = edge ids); pass
- * rel_rowptr == NULL to skip it (it depends on etype only: gn_index_prep(etype)
- * builds the same structure once for every edge list that shares the types). */
-size_t gn_edge_prep_workspace_bytes(int64_t n_edges, int32_t n_nodes, int32_t n_rel);
-int gn_edge_prep(const int64_t* src, const int64_t* dst, const int64_t* etype, int64_t n_edges,
-                 int32_t n_nodes, int32_t n_rel,
-                 int32_t* node_rowptr /*[n_nodes+1]*/, int32_t* ent_other, int32_t* ent_rel, int32_t* ent_eid /*[2E]*/,
-                 int32_t* rel_rowptr /*[n_rel+1]*/, int32_t* rel_eid /*[E]*/,
-                 void* ws, size_t ws_bytes, void* stream);
-
 /* CSR of an index list (rows = nodes, entries = positions in the list) for the
  * deterministic backward of z[node_list] (gripnet/decoder.py:42). */
 size_t gn_index_prep_workspace_bytes(int64_t n, int32_t n_nodes);
@@ -258,16 +246,6 @@ int gn_distmult_fwd(const float* z, int64_t ldz, int32_t D, const float* w,
 /* per-edge upstream coefficient g_e = grad_e * (sigmoid ? s(1-s) : 1) */
 int gn_distmult_coef(const float* grad_out, const float* out, int64_t n_edges, int sigmoid,
                      float* coef, void* stream);
-/* dz[n] = sum over endpoint entries (other, rel, e) of coef[e] * z[other] .* w[rel]  */
-int gn_distmult_bwd_z(const gn_csr* node_csr, const int32_t* ent_other, const int32_t* ent_rel,
-                      const int32_t* ent_eid, const float* coef, const float* z, int64_t ldz,
-                      int32_t D, const float* w, float* dz, int64_t lddz, float* partial, void* stream);
-/* dw[r] = sum_{e in relation r} coef[e] * z[src_e] .* z[dst_e];  rel_eid == NULL: entry s of the relation
- * CSR is edge s (a relation-major edge list, as the reference builds them, GripNet-pose.py:54-56) */
-int gn_distmult_bwd_w(const gn_csr* rel_csr, const int32_t* rel_eid, const int64_t* src,
-                      const int64_t* dst, const float* coef, const float* z, int64_t ldz,
-                      int32_t D, float* dw, float* partial, void* stream);
-
 /* K10 in ONE gather pass.  gn_pair_prep groups the 2E endpoint entries of an edge list by (node, relation):
  * pair_rowptr [n_nodes * n_rel + 1] (row = node * n_rel + rel), entries (other endpoint, edge id) in their
  * original relative order (stable sort).  gn_distmult_bwd_pairs walks it once:

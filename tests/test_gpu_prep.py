@@ -160,22 +160,12 @@ def test_rgcn_prep():
 
 @pytest.mark.parametrize("n,r,e", [(120, 7, 4000), (645, 16, 50000), (1024, 3, 9000), (1500, 300, 20000),
                                    (70000, 2, 30000), (5, 1, 0)])
-def test_edge_and_index_prep(n, r, e):
-    """Endpoint CSR / relation CSR / index CSR, bit-exact vs a stable argsort.  Sizes cover the
+def test_index_prep(n, r, e):
+    """Index CSR (relation lists, labelled-node lists), bit-exact vs a stable argsort.  Sizes cover the
     single-pass path (<= 1024 rows, 8- and 10-bit digits) and the multi-pass radix sort."""
-    from gripnet_b200.graph import EdgeStruct, IndexStruct
+    from gripnet_b200.graph import IndexStruct
     rs = np.random.RandomState(9)
-    ei = rs.randint(0, n, size=(2, e))
     et = rs.randint(0, r, size=e)
-    es = EdgeStruct(torch.from_numpy(ei).to(_dev()), torch.from_numpy(et).to(_dev()), n, r, exact=True)
-    keys = np.concatenate([ei[0], ei[1]])
-    rp, perm = port.csr_from_edges(keys, n)
-    other = np.concatenate([ei[1], ei[0]])[perm]
-    eid = np.where(perm < e, perm, perm - e)
-    assert np.array_equal(es.node.rowptr.cpu().numpy(), rp)
-    assert np.array_equal(es.ent_other[: 2 * e].cpu().numpy(), other)
-    assert np.array_equal(es.ent_eid[: 2 * e].cpu().numpy(), eid)
-    assert np.array_equal(es.ent_rel[: 2 * e].cpu().numpy(), et[eid])
     rel = IndexStruct(torch.from_numpy(et).to(_dev()), r)
     rp_r, perm_r = port.csr_from_edges(et, r)
     assert np.array_equal(rel.csr.rowptr.cpu().numpy(), rp_r)
@@ -185,7 +175,7 @@ def test_edge_and_index_prep(n, r, e):
     st = IndexStruct(torch.from_numpy(idx).to(_dev()), n)
     rp_i, perm_i = port.csr_from_edges(idx, n)
     assert np.array_equal(st.csr.rowptr.cpu().numpy(), rp_i) and np.array_equal(st.perm[:m].cpu().numpy(), perm_i)
-    assert int(st.csr.row_counter.abs().sum()) == 0 and int(es.node.row_counter.abs().sum()) == 0
+    assert int(st.csr.row_counter.abs().sum()) == 0
 
 
 @pytest.mark.parametrize("n_rows", [400, 3000, 20000, 50000])   # one-block builder (<= 32768 rows) and the scan path
