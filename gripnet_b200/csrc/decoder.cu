@@ -234,6 +234,127 @@ __global__ void __launch_bounds__(kGradThreads) distmult_grads_kernel(const floa
   if (threadIdx.x == 0) slab_count[rel] = 0;
 }
 
+// ---- 128-bit variant (D % 4 == 0, D <= 128): CTAs of C4 * 16 threads (C4 = D / 4 float4 columns x 16 sub-rows).
+//   dz CTA: `nodes` nodes x `gr` relation groups (nodes * gr == 16); a sub-row adds the relations gr, gr + GR, ...
+//           of its node with kVU float4 pairs in flight, the GR partial rows are added in group order;
+//   dw CTA: one (relation, slab of kVSlab nodes): 16 sub-rows stride over the slab's nodes, partial rows added in
+//           sub-row order, slabs combined by the last-arriving CTA in slab order (as in the scalar kernel).
+// A few hundred CTAs that each stream contiguous 4*D-byte rows of T, instead of one 1024-thread CTA per node.
+constexpr int kVSub = 16;
+constexpr int kVSlab = 128;
+constexpr int kVU = 4;
+
+__device__ __forceinline__ void f4_fma(float4& a, const float4& x, const float4& y) {
+  a.x = fmaf(x.x, y.x, a.x); a.y = fmaf(x.y, y.y, a.y); a.z = fmaf(x.z, y.z, a.z); a.w = fmaf(x.w, y.w, a.w);
+}
+__device__ __forceinline__ float4 f4_add(const float4& x, const float4& y) {
+  return make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+}
+
+__global__ void __launch_bounds__(512) distmult_grads_vec_kernel(const float* __restrict__ T,
+                                                                 const float* __restrict__ T2, int n_nodes, int n_rel,
+                                                                 int D, const float* __restrict__ z, int64_t ldz,
+                                                                 const float* __restrict__ w, float* __restrict__ dz,
+                                                                 int64_t lddz, float* __restrict__ dw, int n_slabs,
+                                                                 float* __restrict__ slab_part,
+                                                                 unsigned int* __restrict__ slab_count, int gr_count) {
+  extern __shared__ float4 red4[];                     // [kVSub][C4]
+  __shared__ int s_last;
+  const int C4 = D >> 2;
+  const int c4 = int(threadIdx.x) % C4, sub = int(threadIdx.x) / C4;
+  const int n_dw_blocks = dw ? n_rel * n_slabs : 0;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = zero;
+  if (int(blockIdx.x) >= n_dw_blocks) {
+    // ---------------------------------------------------------------- dz rows
+    const int GR = gr_count, nodes = kVSub / GR;
+    const int node = (int(blockIdx.x) - n_dw_blocks) * nodes + sub / GR, g = sub % GR;
+    if (dz == nullptr) return;
+    if (node < n_nodes) {
+      const float4* t1 = reinterpret_cast<const float4*>(T + int64_t(node) * n_rel * D) + c4;
+      const float4* t2 = T2 ? reinterpret_cast<const float4*>(T2 + int64_t(node) * n_rel * D) + c4 : nullptr;
+      const float4* wp = reinterpret_cast<const float4*>(w) + c4;
+      for (int r0 = g; r0 < n_rel; r0 += kVU * GR) {
+        float4 tv[kVU], wv[kVU];
+#pragma unroll
+        for (int u = 0; u < kVU; ++u) {
+          const int r = r0 + u * GR;
+          tv[u] = wv[u] = zero;
+          if (r < n_rel) {
+            tv[u] = __ldg(t1 + int64_t(r) * C4);
+            if (t2) tv[u] = f4_add(tv[u], __ldg(t2 + int64_t(r) * C4));
+            wv[u] = __ldg(wp + int64_t(r) * C4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kVU; ++u) f4_fma(acc, tv[u], wv[u]);
+      }
+    }
+    if (GR > 1) {
+      red4[sub * C4 + c4] = acc;
+      __syncthreads();
+      if (g == 0 && node < n_nodes) {
+        for (int k = 1; k < GR; ++k) acc = f4_add(acc, red4[(sub + k) * C4 + c4]);
+      }
+    }
+    if (g == 0 && node < n_nodes) *reinterpret_cast<float4*>(dz + int64_t(node) * lddz + 4 * c4) = acc;
+    return;
+  }
+  // ------------------------------------------------------------------ dw slab
+  const int rel = int(blockIdx.x) / n_slabs, slab = int(blockIdx.x) % n_slabs;
+  const int n0 = slab * kVSlab;
+  const int n1 = n0 + kVSlab < n_nodes ? n0 + kVSlab : n_nodes;
+  for (int i0 = n0 + sub; i0 < n1; i0 += kVU * kVSub) {
+    float4 tv[kVU], zv[kVU];
+#pragma unroll
+    for (int u = 0; u < kVU; ++u) {
+      const int i = i0 + u * kVSub;
+      tv[u] = zv[u] = zero;
+      if (i < n1) {
+        const int64_t t = (int64_t(i) * n_rel + rel) * C4 + c4;
+        tv[u] = __ldg(reinterpret_cast<const float4*>(T) + t);
+        if (T2) tv[u] = f4_add(tv[u], __ldg(reinterpret_cast<const float4*>(T2) + t));
+        zv[u] = __ldg(reinterpret_cast<const float4*>(z + int64_t(i) * ldz) + c4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kVU; ++u) f4_fma(acc, tv[u], zv[u]);
+  }
+  red4[sub * C4 + c4] = acc;
+  __syncthreads();
+  if (sub == 0) {
+    for (int k = 1; k < kVSub; ++k) acc = f4_add(acc, red4[k * C4 + c4]);
+    if (n_slabs == 1) {
+      *reinterpret_cast<float4*>(dw + int64_t(rel) * D + 4 * c4) =
+          make_float4(0.5f * acc.x, 0.5f * acc.y, 0.5f * acc.z, 0.5f * acc.w);
+    } else {
+      *reinterpret_cast<float4*>(slab_part + (int64_t(rel) * n_slabs + slab) * D + 4 * c4) = acc;
+    }
+  }
+  if (n_slabs == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(slab_count + rel, 1u) == unsigned(n_slabs - 1)) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (sub == 0) {
+    const float4* p = reinterpret_cast<const float4*>(slab_part + int64_t(rel) * n_slabs * D) + c4;
+    float4 t = zero;
+    int k = 0;
+    for (; k + 7 < n_slabs; k += 8) {                 // eight slabs in flight, added in slab order
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcg(p + int64_t(k + u) * C4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t = f4_add(t, v[u]);
+    }
+    for (; k < n_slabs; ++k) t = f4_add(t, __ldcg(p + int64_t(k) * C4));
+    *reinterpret_cast<float4*>(dw + int64_t(rel) * D + 4 * c4) = make_float4(0.5f * t.x, 0.5f * t.y, 0.5f * t.z, 0.5f * t.w);
+  }
+  if (threadIdx.x == 0) slab_count[rel] = 0;
+}
+
 __global__ void pair_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                  const int64_t* __restrict__ etype, int64_t n_edges, int32_t n_rel,
                                  int32_t* __restrict__ key) {
@@ -436,8 +557,14 @@ int gn_distmult_bwd_pairs(const gn_csr* pair_csr, const int32_t* ent_other, cons
   return GN_ERR_ARG;
 }
 
+static bool grads_vec_ok(int D, const float* T, const float* T2, const float* z, int64_t ldz, const float* w,
+                         const float* dz, int64_t lddz, const float* dw) {
+  return D % 4 == 0 && D <= 128 && ldz % 4 == 0 && lddz % 4 == 0 && aligned16(T) && (!T2 || aligned16(T2)) &&
+         aligned16(z) && aligned16(w) && (!dz || aligned16(dz)) && (!dw || aligned16(dw));
+}
+
 size_t gn_distmult_grads_workspace_bytes(int32_t n_nodes, int32_t n_rel, int32_t D) {
-  const size_t slabs = size_t(ceil_div(n_nodes > 0 ? n_nodes : 1, kGradSlabNodes));
+  const size_t slabs = size_t(ceil_div(n_nodes > 0 ? n_nodes : 1, kGradSlabNodes));   // the smaller slab size
   return align_up(size_t(n_rel > 0 ? n_rel : 1) * 4) + size_t(n_rel > 0 ? n_rel : 1) * slabs * size_t(D > 0 ? D : 1) * 4 + 256;
 }
 
@@ -446,7 +573,8 @@ int gn_distmult_grads(const float* T, const float* T2, int32_t n_nodes, int32_t 
                       void* stream) {
   if (n_nodes <= 0 || n_rel <= 0 || D <= 0 || D > kGradThreads || !T || !z || !w || (!dz && !dw)) return GN_ERR_ARG;
   cudaStream_t st = as_stream(stream);
-  const int n_slabs = int(ceil_div(n_nodes, kGradSlabNodes));
+  const bool vec = grads_vec_ok(D, T, T2, z, ldz, w, dz, lddz, dw);
+  const int n_slabs = int(ceil_div(n_nodes, vec ? kVSlab : kGradSlabNodes));
   unsigned int* count = nullptr;
   float* part = nullptr;
   if (dw && n_slabs > 1) {
@@ -454,6 +582,15 @@ int gn_distmult_grads(const float* T, const float* T2, int32_t n_nodes, int32_t 
     count = static_cast<unsigned int*>(ws);
     part = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(size_t(n_rel) * 4));
     if (cudaMemsetAsync(count, 0, size_t(n_rel) * 4, st) != cudaSuccess) return GN_ERR_CUDA;
+  }
+  if (vec) {
+    const int C4 = D / 4;
+    const int GR = n_rel > 32 ? 8 : 1;                       // many relations: eight sub-rows share a node
+    const int nodes_per_cta = kVSub / GR;
+    const int64_t blocks = int64_t(dw ? n_rel * n_slabs : 0) + (dz ? ceil_div(n_nodes, nodes_per_cta) : 0);
+    GN_LAUNCH(distmult_grads_vec_kernel, (unsigned)blocks, C4 * kVSub, size_t(kVSub) * C4 * sizeof(float4), st, T, T2,
+              n_nodes, n_rel, D, z, ldz, w, dz, lddz, dw, n_slabs, part, count, GR);
+    return GN_OK;
   }
   const int G = kGradThreads / D;
   const size_t smem = size_t(G) * size_t(D) * sizeof(float);

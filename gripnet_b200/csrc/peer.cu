@@ -27,6 +27,7 @@ struct PeerArgs {
   char* buf[kMaxPeers];                  // every rank's gather buffer (peer-mapped device pointers)
   unsigned long long* flags[kMaxPeers];  // every rank's flag block: [n_buffers][kMaxPeers]
   char* mc;                              // multicast (NVLS) mapping of the same buffer on ALL ranks, or NULL
+  unsigned long long* mc_flags;          // multicast mapping of the flag block, or NULL
   int world, rank;
   int64_t slot_bytes;
   int flag_index;
@@ -51,16 +52,20 @@ __device__ __forceinline__ void multimem_st16(void* p, const int4& v) {
                : "memory");
 }
 
-__device__ __forceinline__ void red_release_sys_add(unsigned long long* p, unsigned long long v) {
-  asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void red_relaxed_sys_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// one reduction, applied by the NVSwitch to the same word of EVERY rank's flag block
+__device__ __forceinline__ void multimem_red_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Publish / wait round of one exchange.  Flag (buffer b, rank r) in a rank's flag block COUNTS the CTAs of rank
 // r that have delivered their part of buffer b, over all uses of the buffer (u64, never reset).
 //   * every CTA: once its own stores are issued (barrier), ONE thread orders them system-wide (fence.sys, cumulative
-//     over the CTA's stores through the barrier) and adds 1 to its flag in every peer's block with a remote
-//     red.release.sys — no intra-GPU arrival counter, no serial "last CTA" tail: a CTA's signal leaves as soon as
-//     that CTA is done;
+//     over the CTA's stores through the barrier) and adds 1 to its flag in every peer's block — one
+//     multimem.red through the NVSwitch when the arena has a multicast mapping, else world-1 relaxed remote reds —
+//     no intra-GPU arrival counter, no serial "last CTA" tail: a CTA's signal leaves as soon as that CTA is done;
 //   * CTA 0 alone waits: thread p spins (ld.acquire.sys on this rank's OWN memory) until peer p's count reaches
 //     (uses so far + 1) x gridDim.x — every rank launches the same grid for the same buffer, because buffer shapes
 //     are symmetric.  The kernel therefore ends only when every peer's data has arrived, and the kernels behind it
@@ -71,10 +76,14 @@ __device__ __forceinline__ void signal_and_wait(const PeerArgs& a) {
   __syncthreads();
   const int slot = a.flag_index * kMaxPeers;
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    for (int s = 1; s < a.world; ++s) {
-      const int peer = (a.rank + s) % a.world;
-      red_release_sys_add(a.flags[peer] + slot + a.rank, 1ull);
+    __threadfence_system();              // ONE system-scope fence orders the CTA's stores; the signals are relaxed
+    if (a.mc_flags != nullptr) {
+      multimem_red_add(a.mc_flags + slot + a.rank, 1ull);     // one instruction signals every rank
+    } else {
+      for (int s = 1; s < a.world; ++s) {
+        const int peer = (a.rank + s) % a.world;
+        red_relaxed_sys_add(a.flags[peer] + slot + a.rank, 1ull);
+      }
     }
   }
   if (blockIdx.x != 0) return;
@@ -272,6 +281,8 @@ static int fill_peer_args(PeerArgs& a, const uint64_t* arena_base, int32_t world
     a.flags[p] = reinterpret_cast<unsigned long long*>(base + (p < world ? uint64_t(flag_offset) : 0));
   }
   a.mc = arena_base[world] ? reinterpret_cast<char*>(arena_base[world] + uint64_t(buf_offset)) : nullptr;
+  a.mc_flags = arena_base[world] ? reinterpret_cast<unsigned long long*>(arena_base[world] + uint64_t(flag_offset))
+                                 : nullptr;
   a.world = world; a.rank = rank; a.slot_bytes = slot_bytes; a.flag_index = flag_index;
   a.seq = reinterpret_cast<unsigned long long*>(seq);
   a.done = done;
