@@ -36,6 +36,11 @@ class GnPeerSegment(C.Structure):
     _fields_ = [("src", C.c_void_p), ("bytes", C.c_int64), ("slot_offset", C.c_int64), ("peer", C.c_int32)]
 
 
+class GnHaloPeer(C.Structure):
+    """Mirror of ``gn_halo_peer``."""
+    _fields_ = [("idx", C.c_void_p), ("count", C.c_int64), ("dst_row", C.c_int64)]
+
+
 class GnSumSegment(C.Structure):
     """Mirror of ``gn_sum_segment``."""
     _fields_ = [("dst", C.c_void_p), ("n", C.c_int64), ("slot_offset", C.c_int64)]
@@ -111,6 +116,8 @@ SIGNATURES = {
     "gn_nc_metrics": (_INT, [_P, _P, _I64, _I32, _P, _P, _SZ, _P]),
     "gn_peer_max_world": (_INT, []),
     "gn_peer_allgather": (_INT, [_P, _I32, _I32, _I64, _I64, _I64, _I32, _P, _P, _P, _P]),
+    "gn_peer_halo_grid": (_INT, []),
+    "gn_peer_halo_push": (_INT, [_P, _I32, _I32, _I64, _I64, _P, _I32, _P, _I64, _I32, _P, _P, _P, _P]),
     "gn_peer_max_segments": (_INT, []),
     "gn_peer_push": (_INT, [_P, _I32, _I32, _I64, _I64, _P, _I32, _I64, _I32, _P, _P, _P, _P]),
     "gn_slot_sum": (_INT, [_P, _I32, _I64, _P, _I32, _P]),

@@ -197,6 +197,40 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const PeerArgs a, const 
   signal_and_wait(a);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halo-packed exchange (north_star: "all-gather of HALO source-feature rows").  Instead of its whole block a rank
+// sends to peer p only the rows p's CSR actually references (index lists exchanged once at graph-build time),
+// packed contiguously into p's operand buffer behind p's own rows; p's column indices were remapped to the packed
+// positions.  On power-law graphs a rank references 20-50 % of a remote block, so the bytes ENTERING a GPU drop
+// 2-5x against the full slot all-gather (which is ingress-bound: (P-1) blocks in, one block out through NVLS).
+// Fixed grid (the same on every rank), grid-stride over (peer, row) items, then the usual publish / wait round.
+// ---------------------------------------------------------------------------------------------
+struct HaloArgs {
+  const int32_t* idx[kMaxPeers];     // local row ids to send to peer p (device), NULL / count 0 for p == rank
+  int64_t count[kMaxPeers];
+  int64_t dst_row[kMaxPeers];        // first packed row of this rank's region in peer p's buffer
+  const float* src;                  // this rank's rows (the head of its own buffer)
+  int row_f4;                        // float4 per row
+};
+
+__global__ void __launch_bounds__(256) peer_halo_push_kernel(const PeerArgs a, const HaloArgs h) {
+  const int lanes = h.row_f4 < 32 ? h.row_f4 : 32;            // threads that cooperate on one row
+  const int rows_per_cta = 256 / lanes;
+  const int sub = int(threadIdx.x) / lanes, l = int(threadIdx.x) % lanes;
+  for (int s = 1; s < a.world; ++s) {
+    const int peer = (a.rank + s) % a.world;
+    const int32_t* __restrict__ idx = h.idx[peer];
+    const int64_t cnt = h.count[peer];
+    float4* __restrict__ dst = reinterpret_cast<float4*>(a.buf[peer]) + h.dst_row[peer] * h.row_f4;
+    for (int64_t j = int64_t(blockIdx.x) * rows_per_cta + sub; j < cnt; j += int64_t(gridDim.x) * rows_per_cta) {
+      if (sub >= rows_per_cta) break;
+      const float4* __restrict__ srow = reinterpret_cast<const float4*>(h.src) + int64_t(__ldg(idx + j)) * h.row_f4;
+      for (int c = l; c < h.row_f4; c += lanes) dst[j * h.row_f4 + c] = srow[c];
+    }
+  }
+  signal_and_wait(a);
+}
+
 struct SumBatch {
   float* dst[kMaxSegments];
   int64_t n[kMaxSegments];
@@ -354,5 +388,34 @@ extern "C" int gn_slot_sum(const void* buf, int32_t world, int64_t slot_bytes, c
   b.block_first[b.n_segs] = int32_t(blocks);
   GN_LAUNCH(slot_sum_kernel, (unsigned)blocks, 256, 0, as_stream(stream), static_cast<const char*>(buf), world,
             slot_bytes, b);
+  return GN_OK;
+}
+
+extern "C" int gn_peer_halo_grid(void) { return 148 * 2; }
+
+extern "C" int gn_peer_halo_push(const uint64_t* arena_base /*host*/, int32_t world, int32_t rank, int64_t buf_offset,
+                                 int64_t buf_bytes, const float* src_rows, int32_t row_floats,
+                                 const gn_halo_peer* peers /*host, world entries*/, int64_t flag_offset,
+                                 int32_t flag_index, uint64_t* seq, uint32_t* done, uint32_t* abort_flag, void* stream) {
+  if (world == 1) return GN_OK;
+  if (!peers || !src_rows || row_floats <= 0 || row_floats % 4 != 0 ||
+      (reinterpret_cast<uintptr_t>(src_rows) & 15) != 0)
+    return GN_ERR_ARG;
+  PeerArgs a;
+  GN_CHECK(fill_peer_args(a, arena_base, world, rank, buf_offset, (buf_bytes + 15) / 16 * 16, flag_offset, flag_index,
+                          seq, done, abort_flag));
+  a.mc = nullptr;                       // every peer receives a different subset: unicast stores
+  HaloArgs h;
+  for (int p = 0; p < kMaxPeers; ++p) {
+    h.idx[p] = nullptr; h.count[p] = 0; h.dst_row[p] = 0;
+    if (p < world && p != rank) {
+      if (peers[p].count < 0 || peers[p].dst_row < 0 || (peers[p].count > 0 && !peers[p].idx)) return GN_ERR_ARG;
+      if ((peers[p].dst_row + peers[p].count) * int64_t(row_floats) * 4 > buf_bytes) return GN_ERR_ARG;
+      h.idx[p] = peers[p].idx; h.count[p] = peers[p].count; h.dst_row[p] = peers[p].dst_row;
+    }
+  }
+  h.src = src_rows;
+  h.row_f4 = row_floats / 4;
+  GN_LAUNCH(peer_halo_push_kernel, (unsigned)gn_peer_halo_grid(), 256, 0, as_stream(stream), a, h);
   return GN_OK;
 }

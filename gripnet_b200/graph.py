@@ -318,6 +318,73 @@ def part_values(rowptr, col, val, n_rows, row0, dis_src, dis_dst, transpose):
                    "gn_gcn_part_values")
 
 
+HALO_MODE = os.environ.get("GRIPNET_B200_HALO", "auto")      # "auto" | "off" | "force"
+HALO_THRESHOLD = 0.6        # pack when every rank references < 60 % of the remote rows
+
+
+class HaloPlan:
+    """Halo-packed operand layout of one partitioned CSR (``parallel.DistContext.halo_gather``).
+
+    The gathered operand of this rank becomes ``[own block (B rows) | rows of peer 0 it references | peer 1 | ...]``;
+    ``need[q]`` are the (sorted, unique) global columns of peer q's block this rank's rows reference, the CSR's
+    column indices are remapped IN PLACE to the packed positions, and the lists are exchanged once so that every
+    rank knows which of its rows each peer wants (``send_idx[p]``) and where they land there (``dst_row[p]``).
+    Built collectively; ``None`` from ``build`` means the full slot all-gather stays (dense references)."""
+
+    @staticmethod
+    def build(csr, ctx, block, n_cols_global, r0, r1):
+        import torch.distributed as dist
+        if HALO_MODE == "off" or ctx.world == 1:
+            return None
+        dev = csr.col.device
+        world, rank = ctx.world, ctx.rank
+        cols = csr.col[: csr.nnz].long()
+        seen = torch.zeros(world * block, dtype=torch.bool, device=dev)
+        if csr.nnz > 0:
+            seen[cols] = True
+        seen[rank * block:(rank + 1) * block] = False
+        need = [seen[q * block:(q + 1) * block].nonzero().view(-1).to(torch.int32) for q in range(world)]   # local ids in q
+        counts = torch.tensor([int(t.numel()) for t in need], dtype=torch.int64, device=dev)
+        total = int(counts.sum())
+        stats = torch.tensor([total], dtype=torch.int64, device=dev)
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=ctx.group)
+        max_total = int(stats.item())
+        if HALO_MODE != "force" and max_total >= HALO_THRESHOLD * (world - 1) * block:
+            return None
+        plan = HaloPlan()
+        plan.block, plan.world, plan.rank = block, world, rank
+        plan.rows = block + max_total                       # symmetric buffer size: the largest packed operand
+        plan.recv_counts = [int(c) for c in counts.tolist()]
+        offs, off = [], block
+        for q in range(world):
+            offs.append(off)
+            off += plan.recv_counts[q]
+        plan.recv_off = offs
+        # column remap: own block -> [0, B), a referenced remote column -> its packed position
+        lut = torch.full((world * block,), -1, dtype=torch.int32, device=dev)
+        lut[rank * block:(rank + 1) * block] = torch.arange(block, dtype=torch.int32, device=dev)
+        for q in range(world):
+            if q != rank and plan.recv_counts[q]:
+                lut[q * block + need[q].long()] = offs[q] + torch.arange(plan.recv_counts[q], dtype=torch.int32, device=dev)
+        if csr.nnz > 0:
+            csr.col[: csr.nnz] = lut[cols]
+        # tell every peer which of ITS rows this rank wants, and where they go
+        send_counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(send_counts, counts, group=ctx.group)
+        dst_rows = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(dst_rows, torch.tensor(offs, dtype=torch.int64, device=dev), group=ctx.group)
+        plan.send_counts = [int(c) for c in send_counts.tolist()]
+        plan.dst_row = [int(c) for c in dst_rows.tolist()]
+        flat_need = torch.cat(need) if total else torch.empty(0, dtype=torch.int32, device=dev)
+        flat_send = torch.empty(sum(plan.send_counts), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(flat_send, flat_need, output_split_sizes=plan.send_counts,
+                               input_split_sizes=plan.recv_counts, group=ctx.group)
+        plan.send_idx = list(flat_send.split(plan.send_counts))          # local row ids, per destination peer
+        plan.send_flat = flat_send
+        plan.fraction = max_total / float(max((world - 1) * block, 1))
+        return plan
+
+
 class DistGcnGraph:
     """This rank's rows of a destination-partitioned GCN graph (``parallel.py``), built from this rank's
     edges ONLY: the edges whose destination lies in its block give the rows of the dst-sorted CSR
@@ -374,6 +441,9 @@ class DistGcnGraph:
                                                              with_loops, fill, False)
         part_values(rowptr_t, col_t, val_t, self.n_src, s0, dis_src, dis_all, True)
         self.bwd = Csr(rowptr_t, col_t, val_t, self.n_src, ctx.world * self.b_dst, nnz_t)
+        # halo-packed operands where the rows reference only part of the remote blocks (power-law graphs)
+        self.fwd_halo = HaloPlan.build(self.fwd, ctx, self.b_src, spec.n_src, s0, s1)
+        self.bwd_halo = HaloPlan.build(self.bwd, ctx, self.b_dst, spec.n_dst, d0, d1)
         self.nnz = nnz
         self.deg = deg[: self.n_dst]
         self.indeg = (rowptr[1: self.n_dst + 1] - rowptr[: self.n_dst]).to(torch.int32)
@@ -384,6 +454,8 @@ class DistGcnGraph:
 
     def halo_fraction(self):
         """Fraction of the REMOTE operand rows referenced by this rank's forward rows (one pass, cached)."""
+        if self.fwd_halo is not None:
+            return self.fwd_halo.fraction
         if self._halo is None:
             n_cols = self.ctx.world * self.b_src
             seen = torch.zeros(n_cols, dtype=torch.bool, device=self.fwd.col.device)

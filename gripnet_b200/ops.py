@@ -56,13 +56,18 @@ class Slot:
     (``parallel.py``): ``full`` is the ``[world*B, f]`` gather buffer, ``m`` views this rank's slot, so
     the producing kernel writes in place and ``gather()`` completes the buffer with one in-place
     NCCL all-gather (gathered row index == global node id)."""
-    __slots__ = ("m", "full", "dctx")
+    __slots__ = ("m", "full", "dctx", "halo")
 
-    def __init__(self, n_local, f, like, dctx=None, block=None):
-        self.dctx = dctx
+    def __init__(self, n_local, f, like, dctx=None, block=None, halo=None):
+        self.dctx, self.halo = dctx, halo
         if dctx is None:
             t = _new(n_local, f, like)
             self.m, self.full = M(t), M(t)
+        elif halo is not None:
+            # halo-packed operand (graph.HaloPlan): own rows first, then only the referenced rows of each peer
+            buf = dctx.slot_buffer(halo.rows, f, like, uniform=False)
+            self.full = M(buf)
+            self.m = M(buf[:n_local])
         else:
             buf = dctx.slot_buffer(dctx.world * block, f, like)
             self.full = M(buf)
@@ -70,7 +75,10 @@ class Slot:
 
     def gather(self):
         if self.dctx is not None:
-            self.dctx.all_gather_slots(self.full.t)
+            if self.halo is not None:
+                self.dctx.halo_gather(self.full.t, self.halo)
+            else:
+                self.dctx.all_gather_slots(self.full.t)
         return self.full
 
 
@@ -234,7 +242,7 @@ class GcnStack(torch.autograd.Function):
         for l in range(n_layers):
             w = weights[l].contiguous()
             k, f = dims[l], dims[l + 1]
-            y = Slot(graph.n_src, f, x0, dctx, b_src)
+            y = Slot(graph.n_src, f, x0, dctx, b_src, getattr(graph, "fwd_halo", None))
             xin = M(x0) if l == 0 else outs[l]
             sgemm(False, False, graph.n_src, f, k, xin.ptr, xin.ld, w.data_ptr(), f, y.m.ptr, y.m.ld, dev)
             if l == 0 and catout:
@@ -273,6 +281,7 @@ class GcnStack(torch.autograd.Function):
         dev = g.device
         dctx = getattr(graph, "ctx", None)
         b_dst = graph.b_dst if dctx is not None else None
+        bwd_halo = getattr(graph, "bwd_halo", None)
         if catout:
             offs = [sum(dims[:i]) for i in range(len(dims))]
             gs = [M(g, offs[i], dims[i]) for i in range(len(dims))]
@@ -292,10 +301,10 @@ class GcnStack(torch.autograd.Function):
             if dz_slot is not None:
                 dz = dz_slot
             elif relu_flags[l - 1]:
-                dz = Slot(graph.n_dst, f, g, dctx, b_dst)
+                dz = Slot(graph.n_dst, f, g, dctx, b_dst, bwd_halo)
                 relu_bwd(dh, h_l, dz.m)
             elif dctx is not None:
-                dz = Slot(graph.n_dst, f, g, dctx, b_dst)
+                dz = Slot(graph.n_dst, f, g, dctx, b_dst, bwd_halo)
                 map2d(_lib.EW_COPY, dh, dz.m)
             else:
                 dz = Slot.__new__(Slot)
@@ -323,7 +332,7 @@ class GcnStack(torch.autograd.Function):
                 mask = h_prev if (l > 1 and relu_flags[l - 2]) else None
                 # dH_{l-1} = dY W^T (+ concat-slice grad) (masked by ReLU of layer l-1); when it is the
                 # next layer's dZ it is produced straight into that layer's gather slot
-                dprev = Slot(graph.n_src, k, g, dctx if mask is not None else None, b_dst)
+                dprev = Slot(graph.n_src, k, g, dctx if mask is not None else None, b_dst, bwd_halo)
                 sgemm(False, True, graph.n_src, k, f, dy.ptr, dy.ld, w.data_ptr(), f, dprev.m.ptr, dprev.m.ld, dev,
                       addend=addend, mask=mask)
                 dh = dprev.m

@@ -176,14 +176,16 @@ class DistContext:
         """True if a peer-memory gather timed out (one host read; call outside captured regions)."""
         return self.arena is not None and int(self.arena.abort.item()) != 0
 
-    def slot_buffer(self, rows, f, like):
-        """A ``[rows, f]`` fp32 gather buffer (``rows = world * B``): from the symmetric arena when it
-        exists (then ``all_gather_slots`` exchanges it over peer memory), else from the allocator."""
+    def slot_buffer(self, rows, f, like, uniform=True):
+        """A ``[rows, f]`` fp32 gather buffer (``rows = world * B``, or the packed row count of a halo plan with
+        ``uniform=False``): from the symmetric arena when it exists (then ``all_gather_slots`` /
+        ``halo_gather`` exchange it over peer memory), else from the allocator."""
         nbytes = int(rows) * int(f) * 4
         if self.peer_mode == "auto":
             self._step_bytes += (nbytes + 255) // 256 * 256
             self._step_gathers += 1
-            if self.arena is not None and (nbytes // self.world) % 16 == 0 and nbytes % self.world == 0:
+            ok = (nbytes // self.world) % 16 == 0 and nbytes % self.world == 0 if uniform else (int(f) % 4 == 0)
+            if self.arena is not None and ok:
                 tok = self.arena.alloc(nbytes)
                 if tok is not None:
                     t = tok[0].view(torch.float32).view(int(rows), int(f))
@@ -251,6 +253,34 @@ class DistContext:
             return full
         b = full.size(0) // self.world
         dist.all_gather_into_tensor(full, full[self.rank * b:(self.rank + 1) * b], group=self.group)
+        self.nccl_gathers += 1
+        return full
+
+    def halo_gather(self, full, plan):
+        """Complete a halo-packed operand (``graph.HaloPlan``): this rank's rows sit at the head of ``full``; every
+        peer's referenced rows are stored behind them — by ``gn_peer_halo_push`` over NVLink peer memory for arena
+        buffers, by an NCCL all-to-all of the packed rows otherwise (first step / peer mode off)."""
+        tok = self._tokens.get(full.data_ptr())
+        if tok is not None:
+            from . import _lib
+            from .graph import _stream
+            a = self.arena
+            _, offset, index = tok
+            table = (_lib.GnHaloPeer * self.world)()
+            for p in range(self.world):
+                cnt = plan.send_counts[p] if p != self.rank else 0
+                table[p] = _lib.GnHaloPeer(plan.send_idx[p].data_ptr() if cnt else None, cnt, plan.dst_row[p])
+            _lib.check(_lib.load().gn_peer_halo_push(a.bases, self.world, self.rank, offset, full.numel() * 4,
+                                                     full.data_ptr(), full.size(1), ctypes.cast(table, ctypes.c_void_p),
+                                                     0, index, a.seq[index:].data_ptr(), a.done[index:].data_ptr(),
+                                                     a.abort.data_ptr(), _stream()), "gn_peer_halo_push")
+            self.peer_gathers += 1
+            return full
+        send = full[: plan.block].index_select(0, plan.send_flat.long()) if plan.send_flat.numel() else \
+            full.new_empty((0, full.size(1)))
+        recv = full[plan.block: plan.block + sum(plan.recv_counts)]
+        dist.all_to_all_single(recv, send, output_split_sizes=plan.recv_counts, input_split_sizes=plan.send_counts,
+                               group=self.group)
         self.nccl_gathers += 1
         return full
 

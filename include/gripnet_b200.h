@@ -396,6 +396,24 @@ int gn_peer_allgather(const uint64_t* arena_base /*host*/, int32_t world, int32_
                       uint32_t* done, uint32_t* abort_flag, void* stream);
 
 
+/* Halo-packed exchange (north_star: "all-gather of halo source-feature rows").  The operand buffer of a rank is
+ * [its own rows | the rows of peer 0 it references | peer 1 ...] (packed, column indices remapped at graph-build time);
+ * `peers[p]` (HOST array, `world` entries; entry `rank` ignored) tells this call which of ITS rows peer p needs
+ * (`idx`: device int32 local row ids, `count`) and where they go in p's buffer (`dst_row`: first packed row).
+ * The rows are read from `src_rows` (this rank's rows, row_floats floats each, a multiple of 4, 16-byte aligned) and
+ * stored over NVLink; then the publish / wait round of gn_peer_allgather.  Every rank launches the same fixed grid
+ * (gn_peer_halo_grid()).  `buf_bytes` = size of the (symmetric) operand buffer at `buf_offset`. */
+typedef struct {
+  const int32_t* idx;
+  int64_t count;
+  int64_t dst_row;
+} gn_halo_peer;
+int gn_peer_halo_grid(void);
+int gn_peer_halo_push(const uint64_t* arena_base /*host*/, int32_t world, int32_t rank, int64_t buf_offset,
+                      int64_t buf_bytes, const float* src_rows, int32_t row_floats,
+                      const gn_halo_peer* peers /*host*/, int64_t flag_offset, int32_t flag_index, uint64_t* seq,
+                      uint32_t* done, uint32_t* abort_flag, void* stream);
+
 /* Segmented push + rank-ordered sum over the same arena: the small reductions of a partitioned step
  * (bucketed weight-gradient all-reduce + loss, reduce-scatter of the decoder's dz) without NCCL.
  * The exchange buffer is [world][slot_bytes] at `buf_offset` of every arena.  gn_peer_push stores every

@@ -81,10 +81,12 @@ def run_pose(dctx, dev, with_oracle):
     return worst
 
 
-def run_chain(dctx, dev, streamed=False):
+def run_chain(dctx, dev, streamed=False, halo="auto"):
     """``streamed``: every rank keeps only its shard of each generated chunk (no global edge list, no global
-    CSR on any rank) — the way bench.py builds BASELINE config 5."""
+    CSR on any rank) — the way bench.py builds BASELINE config 5.  ``halo="force"``: every partitioned CSR uses
+    the halo-packed operand layout (only referenced remote rows are exchanged), whatever its density."""
     from gripnet_b200 import graph as G
+    G.HALO_MODE = halo
     from gripnet_b200.pipelines import ROW_PARTITIONED, ChainModel, shard_chain, shard_chain_streamed
     from synthdata import chain_small
     g = chain_small(dev)
@@ -103,6 +105,7 @@ def run_chain(dctx, dev, streamed=False):
     loss, z, _ = m(data)
     loss.backward()
     r0, r1 = dctx.bounds(g["n_c"])
+    G.HALO_MODE = "auto"
     worst = max(check("chain z", z, z_g[r0:r1]), check("chain loss", loss, loss_g))
     named_g = dict(ref.named_parameters())
     for k, v in m.named_parameters():
@@ -113,6 +116,53 @@ def run_chain(dctx, dev, streamed=False):
         if k in ROW_PARTITIONED:
             gg = dctx.shard_rows(gg, g[ROW_PARTITIONED[k]])
         worst = max(worst, check("chain grad." + k, v.grad, gg, 2e-5))
+    return worst
+
+
+def run_chain_peer(dctx, dev):
+    """ChainModel with every exchange halo-packed: step 1 runs the NCCL all-to-all fallback, later steps
+    gn_peer_halo_push over the symmetric arena; eager and captured steps must agree bit for bit on z and to
+    rounding on the reduced gradients, and with the single-GPU model within 1e-5."""
+    from gripnet_b200 import graph as G
+    from gripnet_b200.capture import CapturedStep
+    from gripnet_b200.pipelines import ROW_PARTITIONED, ChainModel, shard_chain_streamed
+    from synthdata import chain_small
+    g = chain_small(dev)
+    torch.manual_seed(5)
+    ref = ChainModel(g["n_a"], g["n_b"], g["n_c"], g["n_class"], hid=16, out=8).to(dev)
+    loss_g, z_g, _ = ref(g)
+    G.clear_cache()
+    G.HALO_MODE = "force"
+    data = shard_chain_streamed(chain_small, dctx, dev)
+    m = ChainModel(data["n_a"], data["n_b"], data["n_c"], g["n_class"], hid=16, out=8).to(dev)
+    m.mcip.dist_ctx = dctx
+    sd = {k: (dctx.shard_rows(v, g[ROW_PARTITIONED[k]]).clone() if k in ROW_PARTITIONED else v.clone())
+          for k, v in ref.state_dict().items()}
+    m.load_state_dict(sd)
+    replicated = [v for k, v in m.named_parameters() if k not in ROW_PARTITIONED]
+    snaps = []
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for step in range(3):
+            m.zero_grad(set_to_none=True)
+            out = m(data)
+            out[0].backward()
+            dctx.reduce_gradients(replicated)
+            torch.cuda.synchronize()
+            snaps.append([dctx.loss_value.detach().clone(), out[1].detach().clone()])
+    torch.cuda.synchronize()
+    G.HALO_MODE = "auto"
+    assert not dctx.peer_failed()
+    assert any(getattr(c._graph, "fwd_halo", None) is not None for c in m.aa.conv_list), "halo plan was not built"
+    assert torch.equal(snaps[0][1], snaps[2][1]), "halo push over peer memory differs from the NCCL all-to-all"
+    r0, r1 = dctx.bounds(g["n_c"])
+    worst = max(check("halo chain z", snaps[2][1], z_g[r0:r1]), check("halo chain loss", snaps[2][0].view(()), loss_g))
+    step = CapturedStep(lambda: m(data), m.parameters(), warmup=1, post_backward=lambda: dctx.reduce_gradients(replicated))
+    for _ in range(3):
+        out = step.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out[1].detach(), snaps[2][1])
     return worst
 
 
@@ -187,7 +237,10 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     dctx = DistContext()
     w1 = run_pose(dctx, dev, with_oracle=(rank == 0))
-    w2 = max(run_chain(dctx, dev), run_chain(dctx, dev, streamed=True))
+    w2 = max(run_chain(dctx, dev), run_chain(dctx, dev, streamed=True), run_chain(dctx, dev, halo="force"),
+             run_chain(dctx, dev, streamed=True, halo="off"))
+    if world > 1:        # halo-packed exchange over peer memory (arena steps) and inside a captured step
+        w2 = max(w2, run_chain_peer(DistContext(defer_grad_reduce=True), dev))
     w1 = max(w1, run_pose(DistContext(defer_grad_reduce=True), dev, with_oracle=False))
     peer = (False, 0, 0, 0, 0)
     if world > 1:
