@@ -706,7 +706,7 @@ def config5_record(args, world, rank, dev, dctx, flush, peaks):
     ms = rec["dev_ms"] / steps
     # per-rank algorithmic bytes of one step: every SpMM launch fwd and bwd (E'(8+4F) + N(8+4F)), F = 64 / 32
     model = w["model"]
-    spmm_bytes, gathered = 0, 0
+    spmm_bytes, gathered, halo_used = 0, 0, 0
     halo = []
     for name, layers in (("aa", 2), ("ab", 1), ("bb", 2), ("bc", 1), ("cc", 2)):
         mod = getattr(model, name)
@@ -714,10 +714,12 @@ def config5_record(args, world, rank, dev, dctx, flush, peaks):
         for c in convs:
             gr = c._graph
             F = c.out_channels
-            for csr in (gr.fwd, gr.bwd):
+            for csr, plan in ((gr.fwd, getattr(gr, "fwd_halo", None)), (gr.bwd, getattr(gr, "bwd_halo", None))):
                 spmm_bytes += csr.nnz * (8 + 4 * F) + csr.n_rows * (8 + 4 * F)
-                if world > 1:
-                    gathered += (world - 1) * (csr.n_cols // world) * F * 4
+                if world > 1:       # rows that enter this GPU per launch: the referenced halo rows, or whole blocks
+                    rows_in = sum(plan.recv_counts) if plan is not None else (world - 1) * (csr.n_cols // world)
+                    gathered += rows_in * F * 4
+                    halo_used += plan is not None
         if world > 1 and hasattr(convs[0]._graph, "halo_fraction"):
             halo.append(round(convs[0]._graph.halo_fraction(), 4))
     t_hbm = spmm_bytes / (peaks["hbm_gbs"] * 1e9)
@@ -733,7 +735,10 @@ def config5_record(args, world, rank, dev, dctx, flush, peaks):
                                 "bytes / 770 GB/s NVLink) over all SpMM launches of the step, per rank"},
            "prep": "per-rank: every rank filtered the streamed generator to its own edges and sorted only those "
                    "(no global edge list, no global CSR)" if world > 1 else "single GPU",
-           "remote_operand_rows_referenced": halo or None}
+           "remote_operand_rows_referenced": halo or None,
+           "exchange": None if world == 1 else
+           (f"halo-packed rows over NVLink peer memory (gn_peer_halo_push) for {halo_used} SpMM operands per step, "
+            "full slot all-gather (NVLS multicast) for the others")}
     if world > 1 and args.check_config5:
         out["loss_check"] = partitioned_loss_check(w, rec, dctx, dev, rank, "scaled")
     del w, step

@@ -67,8 +67,8 @@ __device__ __forceinline__ void multimem_red_add(unsigned long long* p, unsigned
 //     multimem.red through the NVSwitch when the arena has a multicast mapping, else world-1 relaxed remote reds —
 //     no intra-GPU arrival counter, no serial "last CTA" tail: a CTA's signal leaves as soon as that CTA is done;
 //   * CTA 0 alone waits: thread p spins (ld.acquire.sys on this rank's OWN memory) until peer p's count reaches
-//     (uses so far + 1) x gridDim.x — every rank launches the same grid for the same buffer, because buffer shapes
-//     are symmetric.  The kernel therefore ends only when every peer's data has arrived, and the kernels behind it
+//     the running total of expected CTAs (`seq` + this launch's gridDim.x) — every rank launches the same grid
+//     for the same use of a buffer, because buffer shapes are symmetric.  The kernel therefore ends only when every peer's data has arrived, and the kernels behind it
 //     on the stream see the complete buffer.
 // Deadlock-free: signalling never waits, and only one CTA per rank spins (bounded, see below).
 __device__ __forceinline__ void signal_and_wait(const PeerArgs& a) {
@@ -87,9 +87,10 @@ __device__ __forceinline__ void signal_and_wait(const PeerArgs& a) {
     }
   }
   if (blockIdx.x != 0) return;
-  if (threadIdx.x == 0) s_use = *a.seq + 1;
+  // `seq` = CTAs every peer has been expected to deliver to this buffer so far (uses may differ in grid size)
+  if (threadIdx.x == 0) s_use = *a.seq + gridDim.x;
   __syncthreads();
-  const unsigned long long target = s_use * gridDim.x;
+  const unsigned long long target = s_use;
   if (threadIdx.x >= 1 && threadIdx.x < a.world) {
     const int peer = (a.rank + int(threadIdx.x)) % a.world;
     const unsigned long long* f = a.flags[a.rank] + slot + peer;

@@ -118,3 +118,37 @@ def test_block_partition_properties():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert all(0 <= hi - lo <= b for lo, hi in spans) and world * b >= n
+
+
+# ------------------------------------------------------------------------------------------------
+def _halo_plan(rank, world):
+    """HaloPlan (graph.py) on CPU tensors over gloo: the packed operand [own rows | referenced rows of each peer]
+    read through the remapped columns equals the full gathered operand read through the global columns, for an
+    uneven partition with rows that reference nothing remote and peers that are not referenced at all."""
+    from types import SimpleNamespace
+    from gripnet_b200 import graph as G
+    from gripnet_b200 import parallel
+    G.HALO_MODE = "force"
+    ctx = parallel.DistContext()
+    n = 23                                            # blocks of 12 and 11 (world 2)
+    b = ctx.block(n)
+    r0, r1 = ctx.bounds(n)
+    rs = np.random.RandomState(7)                     # same global graph on every rank
+    cols_all = [rs.choice(n, size=rs.randint(0, 6), replace=True) for _ in range(n)]
+    mine = cols_all[r0:r1]
+    col = torch.tensor(np.concatenate(mine + [np.array([r0])]).astype(np.int32))       # + one local column
+    csr = SimpleNamespace(col=col.clone(), nnz=col.numel())
+    plan = G.HaloPlan.build(csr, ctx, b, n, r0, r1)
+    assert plan is not None and plan.rows >= b
+    feat = torch.arange(world * b * 3, dtype=torch.float32).view(world * b, 3)          # row g = global node g
+    packed = torch.full((plan.rows, 3), -1.0)
+    packed[: r1 - r0] = feat[r0:r1]
+    ctx.halo_gather(packed, plan)                     # gloo all-to-all of the packed rows
+    assert torch.equal(packed[csr.col.long()], feat[col.long()])
+    # every peer learnt exactly which of its rows this rank needs
+    need = sorted(set(int(c) for c in col.tolist() if not (r0 <= c < r1)))
+    assert sum(plan.recv_counts) == len(need)
+
+
+def test_halo_plan_packs_and_remaps_over_gloo():
+    _spawn("_halo_plan", 29635)
