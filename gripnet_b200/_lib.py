@@ -96,6 +96,7 @@ SIGNATURES = {
     "gn_relu_bwd": (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "gn_abs_bwd": (_INT, [_P, _I64, _P, _I64, _P, _I64, _I64, _I32, _F, _P]),
     "gn_axpby": (_INT, [_P, _I64, _F, _P, _I64, _F, _P, _I64, _I64, _I32, _P]),
+    "gn_zero": (_INT, [_P, _SZ, _P]),
     "gn_mean3": (_INT, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I64, _I32, _P]),
     "gn_colsum_workspace_bytes": (_SZ, [_I64, _I32]),
     "gn_colsum": (_INT, [_P, _I64, _I64, _I32, _P, _P, _SZ, _P]),

@@ -285,6 +285,13 @@ int gn_axpby(const float* a, int64_t lda, float alpha, const float* b, int64_t l
   return GN_OK;
 }
 
+int gn_zero(void* p, size_t bytes, void* stream) {
+  if (bytes == 0) return GN_OK;
+  if (!p) return GN_ERR_ARG;
+  if (cudaMemsetAsync(p, 0, bytes, as_stream(stream)) != cudaSuccess) return GN_ERR_CUDA;
+  return GN_OK;
+}
+
 int gn_mean3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* dst,
              int64_t ldd, int64_t n, int32_t F, void* stream) {
   if (n < 0 || F <= 0) return GN_ERR_ARG;

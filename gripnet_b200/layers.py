@@ -46,6 +46,26 @@ class myGCN(Module):
         self.cached_num_edges = None
         self.reset_parameters()
 
+    # cached graphs hold native handles (ctypes structs over device arrays): they are rebuilt on demand, never
+    # copied or pickled — copy.deepcopy(model) / torch.save(model) keep working after the first forward
+    _TRANSIENT = ("_graph", "_aug", "_graph_source")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._TRANSIENT:
+            if k in state:
+                state[k] = None
+        state["cached_num_edges"] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            setattr(new, k, copy.deepcopy(v, memo))
+        return new
+
     def reset_parameters(self):
         _glorot_uniform_(self.weight)                 # layers.py:42-44
         if self.bias is not None:

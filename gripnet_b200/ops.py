@@ -735,19 +735,29 @@ class DistMultPair(torch.autograd.Function):
     (node, relation) structures (the negatives' one is rebuilt on the device every step).  Backward: ONE
     gather pass per list (``gn_distmult_bwd_pairs``, concurrently) and one kernel that forms
     ``dz = sum_r (T_pos + T_neg)[n,r] .* w[r]`` and ``dw = 1/2 sum_n z[n] .* (T_pos + T_neg)[n,r]``.
+
+    ``rel_lo`` / ``n_rel_local`` (partitioned runs): the edge lists of this call only hold relations
+    ``[rel_lo, rel_lo + n_rel_local)`` and ``edge_type`` is already SHIFTED by ``rel_lo`` — a rank's slice of
+    a relation-major list covers a few relations, and the (node, relation) structures, ``T`` and the gradient
+    kernel then span ``n_rel_local`` relations instead of all of them; the other rows of ``dw`` are zero.
     """
 
     @staticmethod
-    def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid):
+    def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid, rel_lo=0, n_rel_local=None):
         from .graph import pair_struct
-        z, w, pi, et = _distmult_check(z, weight, pos_index, edge_type)
-        _, _, ni, _ = _distmult_check(z, weight, neg_index, edge_type)
+        w_full = _as_rows(weight, "weight").contiguous()
+        r_loc = w_full.size(0) if n_rel_local is None else int(n_rel_local)
+        if rel_lo < 0 or rel_lo + r_loc > w_full.size(0):
+            raise RuntimeError("relation slice out of range")
+        w_loc = w_full[rel_lo: rel_lo + r_loc]
+        z, w, pi, et = _distmult_check(z, w_loc, pos_index, edge_type)
+        _, _, ni, _ = _distmult_check(z, w_loc, neg_index, edge_type)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]      # (grad mode is off inside forward)
         br, br_s = streams.Branch(), streams.Branch()
         if need:
             with br_s(pos_index, neg_index, edge_type):
-                pair_struct(neg_index, edge_type, z.size(0), w.size(0))
-                pair_struct(pos_index, edge_type, z.size(0), w.size(0))      # cached after the first step
+                pair_struct(neg_index, edge_type, z.size(0), r_loc)
+                pair_struct(pos_index, edge_type, z.size(0), r_loc)      # cached after the first step
         with br(z, w, ni, et):
             neg = _distmult_fwd(z, w, ni, et, sigmoid)
         pos = _distmult_fwd(z, w, pi, et, sigmoid)
@@ -756,6 +766,7 @@ class DistMultPair(torch.autograd.Function):
         ctx.sigmoid = bool(sigmoid)
         ctx.keys = (pos_index, neg_index, edge_type)
         ctx.key_versions = tuple(t._version for t in ctx.keys)
+        ctx.rel = (int(rel_lo), r_loc, w_full.size(0))
         ctx.save_for_backward(z, w, pos, neg)
         return pos, neg
 
@@ -765,7 +776,8 @@ class DistMultPair(torch.autograd.Function):
         z, w, pos, neg = ctx.saved_tensors
         pos_key, neg_key, et_key = ctx.keys
         _check_versions(ctx.keys, ctx.key_versions, "pos / neg edge_index or edge_type")
-        n, r = z.size(0), w.size(0)
+        rel_lo, r, r_full = ctx.rel
+        n = z.size(0)
         ps_p = pair_struct(pos_key, et_key, n, r)
         ps_n = pair_struct(neg_key, et_key, n, r)
         g_pos, g_neg = g_pos.contiguous(), g_neg.contiguous()
@@ -779,7 +791,12 @@ class DistMultPair(torch.autograd.Function):
         t_p = _pair_walk(ps_p, coef_p, z)
         br.join()
         dz, dw = _distmult_grads(t_p, t_n, z, w, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        return dz, dw, None, None, None, None
+        if dw is not None and r != r_full:                    # relations outside this rank's slice: zero rows
+            dw_full = torch.empty((r_full, w.size(1)), dtype=torch.float32, device=w.device)
+            _lib.check(_lib.load().gn_zero(dw_full.data_ptr(), dw_full.numel() * 4, _stream()), "gn_zero")
+            map2d(_lib.EW_COPY, M(dw), M(dw_full[rel_lo: rel_lo + r]))
+            dw = dw_full
+        return dz, dw, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------

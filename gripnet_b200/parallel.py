@@ -422,7 +422,14 @@ def lookup(edge_index):
 
 
 def clear_registry():
+    """Forget every partitioned edge list (the registry keeps the key tensors alive: call this when a partitioned
+    graph is dropped, as ``bench.py`` does between workloads)."""
     _registry.clear()
+
+
+def forget_edges(edge_index):
+    """Drop one partitioned edge list from the registry (and let its tensor be freed)."""
+    _registry.pop(_key(edge_index), None)
 
 
 # --------------------------------------------------------------------------

@@ -50,9 +50,11 @@ class PoseModel(Module):
             neg = data["neg_edge_index"] if neg_edge_index is None else neg_edge_index
             n_dec = self.gd.n_target
         else:
-            pos, et = data["dd_edge_index_local"], data["dd_edge_type_local"]
+            # this rank's slice of the relation-major lists covers relations [rel_lo, rel_lo + rel_n) only
+            pos, et = data["dd_edge_index_local"], data["dd_edge_type_shifted"]
             neg = data["neg_edge_index_local"] if neg_edge_index is None else neg_edge_index
             n_dec = dctx.world * dctx.block(data["n_d_global"])
+            rel_lo, rel_n = data["dd_rel_lo"], data["dd_rel_n"]
         # the decoder backward's (node, relation) structures depend on the edge lists only — the negatives' one is
         # rebuilt every step (GripNet-pose.py:131 resamples them): it runs on a side stream next to the embedding
         # pass instead of the decoder waiting for it.  It is forked right AFTER the first supervertex has been
@@ -62,8 +64,8 @@ class PoseModel(Module):
         def fork_prep():
             if torch.is_grad_enabled():
                 with prep(pos, neg, et):
-                    G.pair_struct(neg, et, n_dec, self.dmt.num_et)
-                    G.pair_struct(pos, et, n_dec, self.dmt.num_et)
+                    G.pair_struct(neg, et, n_dec, self.dmt.num_et if dctx is None else rel_n)
+                    G.pair_struct(pos, et, n_dec, self.dmt.num_et if dctx is None else rel_n)
 
         z = self.embed(data, after_first=fork_prep)
         prep.join()
@@ -71,7 +73,7 @@ class PoseModel(Module):
             pos_score, neg_score = self.dmt.score_pair(z, pos, neg, et)
             return link_prediction_loss(pos_score, neg_score), z, pos_score, neg_score
         z_full = parallel.all_gather_rows(z, dctx, data["n_d_global"])
-        pos_score, neg_score = self.dmt.score_pair(z_full, pos, neg, et)
+        pos_score, neg_score = self.dmt.score_pair(z_full, pos, neg, et, rel_lo=rel_lo, n_rel_local=rel_n)
         loss = parallel.global_mean_loss(link_prediction_loss(pos_score, neg_score), pos_score.numel(),
                                          data["e_dd_global"], dctx)
         return loss, z, pos_score, neg_score
@@ -166,7 +168,12 @@ def shard_pose(g, dctx, device):
     parallel.distribute_edges(d["dd_edge_index"], dctx, n_d)
     e = g["dd_edge_index"].shape[1]
     e0, e1 = dctx.edge_slice(e)
+    et_loc = g["dd_edge_type"][e0:e1]
+    rel_lo = int(et_loc.min()) if e1 > e0 else 0
+    rel_n = (int(et_loc.max()) - rel_lo + 1) if e1 > e0 else 1
     d.update({
+        "dd_rel_lo": rel_lo, "dd_rel_n": rel_n,
+        "dd_edge_type_shifted": (d["dd_edge_type"][e0:e1] - rel_lo).contiguous(),
         "dist": dctx, "n_g_global": n_g, "n_d_global": n_d, "e_dd_global": e,
         "n_g": dctx.local_count(n_g), "n_d": dctx.local_count(n_d), "edge_slice": (e0, e1),
         "dd_edge_index_local": d["dd_edge_index"][:, e0:e1].contiguous(),

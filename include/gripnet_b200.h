@@ -289,6 +289,8 @@ int gn_abs_bwd(const float* g, int64_t ldg, const float* t, int64_t ldt, float* 
  * — the (x + u) / 2 mixes of interGraph, layers.py:379/382-384 */
 int gn_axpby(const float* a, int64_t lda, float alpha, const float* b, int64_t ldb, float beta,
              float* dst, int64_t ldd, int64_t n, int32_t F, void* stream);
+/* zero-fill (stream-ordered memset; gradient rows no kernel writes) */
+int gn_zero(void* p, size_t bytes, void* stream);
 /* dst = ((a + b) + c) / 3 — the three-way mix of the freebase-d model, GripNet-freebase-d.py:160-161
  * (same association order, true division) */
 int gn_mean3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc,

@@ -86,3 +86,25 @@ def test_install_as_gripnet_aliases_the_reference_import_names():
         for k in [k for k in sys.modules if k == "gripnet" or k.startswith("gripnet.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_modules_copy_and_pickle_without_their_native_graph_handles():
+    """cached graphs hold ctypes handles; deepcopy / pickle must drop them, not choke on them."""
+    import copy
+    import io
+    import torch
+    import gripnet_b200 as gb
+    conv = gb.myGCN(8, 4, cached=True)
+    conv._graph, conv._aug, conv._graph_source, conv.cached_num_edges = object(), None, (None, 3, None), 5   # stand-ins
+    c2 = copy.deepcopy(conv)
+    assert c2._graph is None and c2.cached_num_edges is None and torch.equal(c2.weight, conv.weight)
+    assert c2.weight is not conv.weight
+    buf = io.BytesIO()
+    torch.save(conv, buf)
+    buf.seek(0)
+    c3 = torch.load(buf, weights_only=False)
+    assert c3._graph is None and torch.equal(c3.weight, conv.weight)
+    h = gb.homoGraph([8, 4, 4], start_graph=True, in_dim=10)
+    h.conv_list[0]._graph = object()
+    h2 = copy.deepcopy(h)
+    assert h2.conv_list[0]._graph is None and sorted(h2.state_dict()) == sorted(h.state_dict())
