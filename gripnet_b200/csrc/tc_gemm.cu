@@ -103,17 +103,22 @@ __global__ void __launch_bounds__(256) b_image_kernel(const BView bv, int K, int
 // ---------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full_bar[3], empty_bar[3], acc_bar;
+  __shared__ uint64_t full_bar[3], empty_bar[3], acc_bar, acc_free;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
   const int tile_n = blockIdx.y;
   const int nt = p.nt;
   const int S = p.stages;
   const int stage_sz = stage_bytes(nt);
+  // PERSISTENT over M tiles: this CTA handles tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The barriers, the TMEM
+  // allocation and the stage ring live across tiles (k-block counter `it` keeps running), the loaders fetch the
+  // first k-block of the NEXT tile before they turn into the epilogue of the current one, so the fixed per-tile
+  // latencies (allocation, barrier set-up, first global round trip) are paid once per CTA instead of once per tile.
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int my_tiles = (m_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -121,6 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
+    mbar_init(&acc_free, kLoaderThreads);
     fence_barrier_init();
   }
   if (warp == kLoaderWarps) {  // TMEM allocation by the MMA warp (whole warp, .sync.aligned)
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
     const int c = threadIdx.x & 7;           // k-chunk of this thread
     const int r_base = threadIdx.x >> 3;     // rows r_base + 32*i
     float4 cur[4], nxt[4];
-    auto issue = [&](int kb, float4(&dst)[4]) {
+    auto issue = [&](int m0, int kb, float4(&dst)[4]) {
       const int k = kb * BK + c * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -147,81 +153,87 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
         else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    issue(0, cur);
-    for (int kb = 0; kb < p.n_kb; ++kb) {
-      const int s = kb % S, use = kb / S;
-      if (kb + 1 < p.n_kb) issue(kb + 1, nxt);
-      if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-      unsigned char* a_hi = smem + s * stage_sz;
-      unsigned char* a_lo = a_hi + part_bytes(BM);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 hi, lo;
-        split4(cur[i], hi, lo);
-        const int off = c * plane_bytes(BM) + (r_base + 32 * i) * 16;
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        *reinterpret_cast<float4*>(a_lo + off) = lo;
-      }
-      fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core
-      mbar_arrive(&full_bar[s]);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
-    }
-    // =============================== epilogue ================================
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
     const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
     const int halves = (warp >> 2);                    // 0: low column half, 1: high column half
-    const int row = quarter * 32 + lane;
-    const int m = m0 + row;
     const int n_tile0 = tile_n * nt;
     const int groups = nt / 16;                        // 16-column groups in this tile
     const int g_begin = halves * ((groups + 1) / 2);
     const int g_end = halves ? groups : (groups + 1) / 2;
-    for (int g = g_begin; g < g_end; ++g) {
-      // cross-term accumulators first (small), then the hi*hi ones: round-to-nearest fp32 adds
-      uint32_t r[16];
-      tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(p.n_acc * nt + g * 16), r);
-      for (int a = 1; a < 2 * p.n_acc; ++a) {
-        const int col = (a < p.n_acc ? p.n_acc + a : a - p.n_acc) * nt + g * 16;
-        uint32_t r2[16];
-        tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(col), r2);
+    if (my_tiles > 0) issue(int(blockIdx.x) * BM, 0, cur);
+    for (int t = 0; t < my_tiles; ++t) {
+      const int m0 = (int(blockIdx.x) + t * int(gridDim.x)) * BM;
+      for (int kb = 0; kb < p.n_kb; ++kb) {
+        const int it = t * p.n_kb + kb;
+        const int s = it % S, use = it / S;
+        if (kb + 1 < p.n_kb) issue(m0, kb + 1, nxt);
+        else if (t + 1 < my_tiles) issue(m0 + int(gridDim.x) * BM, 0, nxt);   // next tile: in flight during the epilogue
+        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+        unsigned char* a_hi = smem + s * stage_sz;
+        unsigned char* a_lo = a_hi + part_bytes(BM);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        for (int i = 0; i < 4; ++i) {
+          float4 hi, lo;
+          split4(cur[i], hi, lo);
+          const int off = c * plane_bytes(BM) + (r_base + 32 * i) * 16;
+          *reinterpret_cast<float4*>(a_hi + off) = hi;
+          *reinterpret_cast<float4*>(a_lo + off) = lo;
+        }
+        fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core
+        mbar_arrive(&full_bar[s]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
       }
-      if (m >= p.M) continue;
-      const int n_first = n_tile0 + g * 16;
+      // =============================== epilogue of tile t ================================
+      mbar_wait(&acc_bar, t & 1);
+      tc_fence_after();
+      const int row = quarter * 32 + lane;
+      const int m = m0 + row;
+      for (int g = g_begin; g < g_end; ++g) {
+        // cross-term accumulators first (small), then the hi*hi ones: round-to-nearest fp32 adds
+        uint32_t r[16];
+        tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(p.n_acc * nt + g * 16), r);
+        for (int a = 1; a < 2 * p.n_acc; ++a) {
+          const int col = (a < p.n_acc ? p.n_acc + a : a - p.n_acc) * nt + g * 16;
+          uint32_t r2[16];
+          tmem_ld16(tmem_acc + (uint32_t(quarter * 32) << 16) + uint32_t(col), r2);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int n = n_first + q * 4;
-        if (n >= p.N) break;
-        float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
-                               __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-        if (n + 3 < p.N) {
-          if (p.addend) {
-            const float4 a = *reinterpret_cast<const float4*>(p.addend + int64_t(m) * p.ldd + n);
-            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-          }
-          if (p.mask) {
-            const float4 k = *reinterpret_cast<const float4*>(p.mask + int64_t(m) * p.ldm + n);
-            if (!(k.x > 0.f)) v.x = 0.f;
-            if (!(k.y > 0.f)) v.y = 0.f;
-            if (!(k.z > 0.f)) v.z = 0.f;
-            if (!(k.w > 0.f)) v.w = 0.f;
-          }
-          *reinterpret_cast<float4*>(p.C + int64_t(m) * p.ldc + n) = v;
-        } else {
-          const float vv[4] = {v.x, v.y, v.z, v.w};
-          for (int e = 0; e < 4 && n + e < p.N; ++e) {
-            float x = vv[e];
-            if (p.addend) x += p.addend[int64_t(m) * p.ldd + n + e];
-            if (p.mask && !(p.mask[int64_t(m) * p.ldm + n + e] > 0.f)) x = 0.f;
-            p.C[int64_t(m) * p.ldc + n + e] = x;
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+        }
+        if (m >= p.M) continue;
+        const int n_first = n_tile0 + g * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = n_first + q * 4;
+          if (n >= p.N) break;
+          float4 v = make_float4(__uint_as_float(r[q * 4 + 0]), __uint_as_float(r[q * 4 + 1]),
+                                 __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+          if (n + 3 < p.N) {
+            if (p.addend) {
+              const float4 a = *reinterpret_cast<const float4*>(p.addend + int64_t(m) * p.ldd + n);
+              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            if (p.mask) {
+              const float4 k = *reinterpret_cast<const float4*>(p.mask + int64_t(m) * p.ldm + n);
+              if (!(k.x > 0.f)) v.x = 0.f;
+              if (!(k.y > 0.f)) v.y = 0.f;
+              if (!(k.z > 0.f)) v.z = 0.f;
+              if (!(k.w > 0.f)) v.w = 0.f;
+            }
+            *reinterpret_cast<float4*>(p.C + int64_t(m) * p.ldc + n) = v;
+          } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            for (int e = 0; e < 4 && n + e < p.N; ++e) {
+              float x = vv[e];
+              if (p.addend) x += p.addend[int64_t(m) * p.ldd + n + e];
+              if (p.mask && !(p.mask[int64_t(m) * p.ldm + n + e] > 0.f)) x = 0.f;
+              p.C[int64_t(m) * p.ldc + n + e] = x;
+            }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&acc_free);                // the accumulators may be overwritten by the next tile's MMAs
     }
-    tc_fence_before();
   } else if (warp == kLoaderWarps) {
     // =============================== MMA issuer ==============================
     if (lane == 0) {
@@ -230,32 +242,39 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
       // The tensor core truncates when it adds into the fp32 accumulator, so the error of one
       // accumulator grows linearly with K: long reductions are cut into runs of kb_per_acc
       // k-blocks, each with its own TMEM accumulator pair.
-      uint32_t accumulate = 0;
-      for (int kb = 0; kb < p.n_kb; ++kb) {
-        const int s = kb % S, use = kb / S;
-        const uint32_t tmem_d = tmem_acc + uint32_t((kb / p.kb_per_acc) * nt);              // hi*hi
-        const uint32_t tmem_x = tmem_acc + uint32_t((p.n_acc + kb / p.kb_per_acc) * nt);    // lo*hi + hi*lo
-        if (kb % p.kb_per_acc == 0) accumulate = 0;
-        mbar_wait(&full_bar[s], use & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * stage_sz);
-        const uint32_t a_lo = a_hi + part_bytes(BM);
-        const uint32_t b_hi = a_lo + part_bytes(BM);
-        const uint32_t b_lo = b_hi + part_bytes(nt);
-        const int k_left = p.K - kb * BK;
-        const int ksteps = k_left >= BK ? BK / 8 : (k_left + 7) / 8;
-        for (int j = 0; j < ksteps; ++j) {
-          const uint32_t ao = 2 * j * lbo_a, bo = 2 * j * lbo_b;
-          const uint64_t dah = make_desc(a_hi + ao, lbo_a, 128), dal = make_desc(a_lo + ao, lbo_a, 128);
-          const uint64_t dbh = make_desc(b_hi + bo, lbo_b, 128), dbl = make_desc(b_lo + bo, lbo_b, 128);
-          umma_tf32(tmem_x, dal, dbh, idesc, accumulate);
-          umma_tf32(tmem_x, dah, dbl, idesc, 1);
-          umma_tf32(tmem_d, dah, dbh, idesc, accumulate);
-          accumulate = 1;
+      for (int t = 0; t < my_tiles; ++t) {
+        if (t > 0) {                         // the epilogue of the previous tile has read the accumulators
+          mbar_wait(&acc_free, (t - 1) & 1);
+          tc_fence_after();
         }
-        umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          const int it = t * p.n_kb + kb;
+          const int s = it % S, use = it / S;
+          const uint32_t tmem_d = tmem_acc + uint32_t((kb / p.kb_per_acc) * nt);              // hi*hi
+          const uint32_t tmem_x = tmem_acc + uint32_t((p.n_acc + kb / p.kb_per_acc) * nt);    // lo*hi + hi*lo
+          if (kb % p.kb_per_acc == 0) accumulate = 0;
+          mbar_wait(&full_bar[s], use & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * stage_sz);
+          const uint32_t a_lo = a_hi + part_bytes(BM);
+          const uint32_t b_hi = a_lo + part_bytes(BM);
+          const uint32_t b_lo = b_hi + part_bytes(nt);
+          const int k_left = p.K - kb * BK;
+          const int ksteps = k_left >= BK ? BK / 8 : (k_left + 7) / 8;
+          for (int j = 0; j < ksteps; ++j) {
+            const uint32_t ao = 2 * j * lbo_a, bo = 2 * j * lbo_b;
+            const uint64_t dah = make_desc(a_hi + ao, lbo_a, 128), dal = make_desc(a_lo + ao, lbo_a, 128);
+            const uint64_t dbh = make_desc(b_hi + bo, lbo_b, 128), dbl = make_desc(b_lo + bo, lbo_b, 128);
+            umma_tf32(tmem_x, dal, dbh, idesc, accumulate);
+            umma_tf32(tmem_x, dah, dbl, idesc, 1);
+            umma_tf32(tmem_d, dah, dbh, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(&empty_bar[s]);        // stage reusable once these MMAs have read it
+        }
+        umma_commit(&acc_bar);               // accumulators of tile t complete
       }
-      umma_commit(&acc_bar);               // accumulator complete
     }
     __syncwarp();
   } else {
@@ -265,45 +284,52 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const Params p) {
       if (lane == 0) {
         const uint32_t bytes = 2 * part_bytes(nt);
         const char* src = p.b_image + int64_t(tile_n) * p.n_kb * bytes;
-        for (int kb = 0; kb < p.n_kb; ++kb) {
-          const int s = kb % S, use = kb / S;
-          if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-          mbar_arrive_expect_tx(&full_bar[s], bytes);
-          bulk_g2s(smem + s * stage_sz + 2 * part_bytes(BM), src + int64_t(kb) * bytes, bytes, &full_bar[s]);
+        for (int t = 0; t < my_tiles; ++t) {
+          for (int kb = 0; kb < p.n_kb; ++kb) {
+            const int it = t * p.n_kb + kb;
+            const int s = it % S, use = it / S;
+            if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+            mbar_arrive_expect_tx(&full_bar[s], bytes);
+            bulk_g2s(smem + s * stage_sz + 2 * part_bytes(BM), src + int64_t(kb) * bytes, bytes, &full_bar[s]);
+          }
         }
       }
     } else {
       // small B (a layer's weight matrix, a few KB, L2-resident): this warp splits the k-block's slice of
       // op(B) straight into the stage — no prep kernel, no extra launch on the step's dependency chain
       const int n_tile0 = tile_n * nt;
-      for (int kb = 0; kb < p.n_kb; ++kb) {
-        const int s = kb % S, use = kb / S;
-        if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-        unsigned char* b_hi = smem + s * stage_sz + 2 * part_bytes(BM);
-        unsigned char* b_lo = b_hi + part_bytes(nt);
-        for (int i = lane; i < CHUNKS * nt; i += 32) {
-          const int row = i % nt, c = i / nt;
-          const int n = n_tile0 + row, k = kb * BK + c * 4;
-          float v[4];
+      for (int t = 0; t < my_tiles; ++t) {
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          const int it = t * p.n_kb + kb;
+          const int s = it % S, use = it / S;
+          if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+          unsigned char* b_hi = smem + s * stage_sz + 2 * part_bytes(BM);
+          unsigned char* b_lo = b_hi + part_bytes(nt);
+          for (int i = lane; i < CHUNKS * nt; i += 32) {
+            const int row = i % nt, c = i / nt;
+            const int n = n_tile0 + row, k = kb * BK + c * 4;
+            float v[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = 0.f;
-            if (n < p.N && k + e < p.K)
-              x = p.transB ? __ldg(p.B + int64_t(n) * p.ldb + k + e) : __ldg(p.B + int64_t(k + e) * p.ldb + n);
-            v[e] = x;
+            for (int e = 0; e < 4; ++e) {
+              float x = 0.f;
+              if (n < p.N && k + e < p.K)
+                x = p.transB ? __ldg(p.B + int64_t(n) * p.ldb + k + e) : __ldg(p.B + int64_t(k + e) * p.ldb + n);
+              v[e] = x;
+            }
+            float4 hi, lo;
+            split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+            *reinterpret_cast<float4*>(b_hi + c * plane_bytes(nt) + row * 16) = hi;
+            *reinterpret_cast<float4*>(b_lo + c * plane_bytes(nt) + row * 16) = lo;
           }
-          float4 hi, lo;
-          split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
-          *reinterpret_cast<float4*>(b_hi + c * plane_bytes(nt) + row * 16) = hi;
-          *reinterpret_cast<float4*>(b_lo + c * plane_bytes(nt) + row * 16) = lo;
+          fence_proxy_async();               // generic-proxy stores -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
         }
-        fence_proxy_async();               // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
       }
     }
     __syncwarp();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == kLoaderWarps) {
     tc_fence_after();
@@ -367,6 +393,16 @@ static int tc_set_smem_attr() {
   return GN_OK;
 }
 
+// CTAs along M: persistent over the M tiles — as many CTAs as can be resident (two per SM when shared memory and
+// TMEM allow it), each walking its tiles with a stride of the grid
+static unsigned tc_grid_x(int M, const tc::Plan& pl) {
+  const int64_t m_tiles = ceil_div(M, tc::BM);
+  const int per_sm = (2 * pl.smem_bytes <= 220 * 1024 && 2 * pl.tmem_cols <= 512) ? 2 : 1;
+  int64_t resident = int64_t(148) * per_sm / pl.n_tiles;
+  if (resident < 1) resident = 1;
+  return unsigned(m_tiles < resident ? m_tiles : resident);
+}
+
 // B small enough for the B-producer warp to split it inside the main kernel (one N tile, <= 16 float4 per lane
 // and k-block): no prep launch.  Larger B (the [in, R*out] relation transform of pose-2) keeps the image.
 static bool b_direct(const tc::Plan& pl) { return pl.n_tiles == 1 && pl.nt <= 64; }
@@ -406,7 +442,7 @@ extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const flo
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
   p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
   GN_CHECK(tc_set_smem_attr());
-  dim3 grid((unsigned)ceil_div(M, tc::BM), (unsigned)pl.n_tiles);
+  dim3 grid(tc_grid_x(M, pl), (unsigned)pl.n_tiles);
   GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
   return GN_OK;
 }
@@ -459,7 +495,7 @@ extern "C" int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, co
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
   p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
   GN_CHECK(tc_set_smem_attr());
-  dim3 grid((unsigned)ceil_div(M, tc::BM), (unsigned)pl.n_tiles);
+  dim3 grid(tc_grid_x(M, pl), (unsigned)pl.n_tiles);
   GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
   return GN_OK;
 }
