@@ -48,6 +48,7 @@ struct Params {
   int tmem_cols;
   int n_acc;             // TMEM accumulator PAIRS (hi*hi | cross terms); each covers kb_per_acc k-blocks
   int kb_per_acc;
+  int b_resident;        // the whole split image of this N tile of B stays in shared memory for every M tile
 };
 
 // ---------------------------------------------------------------------------------------
@@ -105,14 +106,19 @@ __global__ void __launch_bounds__(256) b_image_kernel(const BView bv, int K, int
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full_bar[3], empty_bar[3], acc_bar, acc_free;
+  __shared__ uint64_t full_bar[3], empty_bar[3], acc_bar, acc_free, b_ready;
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile_n = blockIdx.y;
   const int nt = p.nt;
   const int S = p.stages;
-  const int stage_sz = stage_bytes(nt);
+  // B RESIDENT (the usual case: K*N*8 bytes of hi/lo image fit next to the A stages): B is split / copied ONCE per
+  // CTA into its own region behind the stages and every M tile of the persistent loop multiplies against it; the
+  // stages then hold A only.  Otherwise B streams through the stages k-block by k-block, for every tile.
+  const int stage_sz = p.b_resident ? 2 * part_bytes(BM) : stage_bytes(nt);
+  unsigned char* b_res = smem + S * stage_sz;
+  const int b_kb_bytes = 2 * part_bytes(nt);
   // PERSISTENT over M tiles: this CTA handles tiles blockIdx.x, blockIdx.x + gridDim.x, ...  The barriers, the TMEM
   // allocation and the stage ring live across tiles (k-block counter `it` keeps running), the loaders fetch the
   // first k-block of the NEXT tile before they turn into the epilogue of the current one, so the fixed per-tile
@@ -122,11 +128,12 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], kLoaderThreads + 1);
+      mbar_init(&full_bar[s], kLoaderThreads + (p.b_resident ? 0 : 1));
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
     mbar_init(&acc_free, kLoaderThreads);
+    mbar_init(&b_ready, 1);
     fence_barrier_init();
   }
   if (warp == kLoaderWarps) {  // TMEM allocation by the MMA warp (whole warp, .sync.aligned)
@@ -242,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
       // The tensor core truncates when it adds into the fp32 accumulator, so the error of one
       // accumulator grows linearly with K: long reductions are cut into runs of kb_per_acc
       // k-blocks, each with its own TMEM accumulator pair.
+      if (p.b_resident && my_tiles > 0) mbar_wait(&b_ready, 0);
       for (int t = 0; t < my_tiles; ++t) {
         if (t > 0) {                         // the epilogue of the previous tile has read the accumulators
           mbar_wait(&acc_free, (t - 1) & 1);
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + s * stage_sz);
           const uint32_t a_lo = a_hi + part_bytes(BM);
-          const uint32_t b_hi = a_lo + part_bytes(BM);
+          const uint32_t b_hi = p.b_resident ? smem_u32(b_res + kb * b_kb_bytes) : a_lo + part_bytes(BM);
           const uint32_t b_lo = b_hi + part_bytes(nt);
           const int k_left = p.K - kb * BK;
           const int ksteps = k_left >= BK ? BK / 8 : (k_left + 7) / 8;
@@ -279,7 +287,45 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
     __syncwarp();
   } else {
     // =============================== B producer ===============================
-    if (p.b_image != nullptr) {
+    if (p.b_resident && my_tiles > 0) {
+      if (p.b_image != nullptr) {
+        // the pre-split image of this N tile: all its k-blocks are contiguous -> bulk async copies of <= 64 KB
+        if (lane == 0) {
+          const uint32_t total = uint32_t(p.n_kb) * uint32_t(b_kb_bytes);
+          const char* src = p.b_image + int64_t(tile_n) * total;
+          mbar_arrive_expect_tx(&b_ready, total);
+          for (uint32_t off = 0; off < total; off += 65536) {
+            const uint32_t bytes = total - off < 65536 ? total - off : 65536;
+            bulk_g2s(b_res + off, src + off, bytes, &b_ready);
+          }
+        }
+      } else {
+        const int n_tile0 = tile_n * nt;
+        for (int kb = 0; kb < p.n_kb; ++kb) {
+          unsigned char* b_hi = b_res + kb * b_kb_bytes;
+          unsigned char* b_lo = b_hi + part_bytes(nt);
+          for (int i = lane; i < CHUNKS * nt; i += 32) {
+            const int row = i % nt, c = i / nt;
+            const int n = n_tile0 + row, k = kb * BK + c * 4;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = 0.f;
+              if (n < p.N && k + e < p.K)
+                x = p.transB ? __ldg(p.B + int64_t(n) * p.ldb + k + e) : __ldg(p.B + int64_t(k + e) * p.ldb + n);
+              v[e] = x;
+            }
+            float4 hi, lo;
+            split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+            *reinterpret_cast<float4*>(b_hi + c * plane_bytes(nt) + row * 16) = hi;
+            *reinterpret_cast<float4*>(b_lo + c * plane_bytes(nt) + row * 16) = lo;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_ready);
+      }
+    } else if (p.b_image != nullptr) {
       // large B: ONE bulk async copy per k-block of the image a prep kernel split beforehand
       if (lane == 0) {
         const uint32_t bytes = 2 * part_bytes(nt);
@@ -339,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
 
 struct Plan {
   bool ok;
-  int nt, n_tiles, n_kb, stages, tmem_cols, n_acc, kb_per_acc;
+  int nt, n_tiles, n_kb, stages, tmem_cols, n_acc, kb_per_acc, b_resident;
   size_t image_bytes, smem_bytes;
 };
 
@@ -363,7 +409,17 @@ static Plan make_plan(int M, int N, int K, int nt_cap = kMaxNt) {
   const int cols = 2 * pl.n_acc * pl.nt;
   pl.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
   pl.image_bytes = size_t(pl.n_tiles) * pl.n_kb * 2 * part_bytes(pl.nt);
-  pl.smem_bytes = size_t(pl.stages) * stage_bytes(pl.nt);
+  // resident B: the A ring is independent of n_kb (it keeps turning across the tiles of the persistent loop):
+  // two stages when that lets two CTAs share an SM, else three if they fit
+  const size_t b_bytes = size_t(pl.n_kb) * 2 * part_bytes(pl.nt);
+  const size_t a_stage = 2 * size_t(part_bytes(BM));
+  int res_stages = 0;
+  if (2 * a_stage + b_bytes <= 110 * 1024) res_stages = 2;
+  else if (3 * a_stage + b_bytes <= 200 * 1024) res_stages = 3;
+  else if (2 * a_stage + b_bytes <= 200 * 1024) res_stages = 2;
+  pl.b_resident = res_stages > 0 ? 1 : 0;
+  if (pl.b_resident) pl.stages = res_stages;
+  pl.smem_bytes = pl.b_resident ? size_t(pl.stages) * a_stage + b_bytes : size_t(pl.stages) * stage_bytes(pl.nt);
   pl.ok = pl.smem_bytes <= 200 * 1024;
   return pl;
 }
@@ -440,7 +496,7 @@ extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const flo
   p.b_image = direct ? nullptr : static_cast<const char*>(ws);
   p.B = B; p.ldb = ldb; p.transB = transB ? 1 : 0;
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
-  p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
+  p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc; p.b_resident = pl.b_resident;
   GN_CHECK(tc_set_smem_attr());
   dim3 grid(tc_grid_x(M, pl), (unsigned)pl.n_tiles);
   GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
@@ -493,7 +549,7 @@ extern "C" int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, co
   p.b_image = static_cast<const char*>(ws);
   p.B = W; p.ldb = f; p.transB = 0;
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
-  p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc;
+  p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc; p.b_resident = pl.b_resident;
   GN_CHECK(tc_set_smem_attr());
   dim3 grid(tc_grid_x(M, pl), (unsigned)pl.n_tiles);
   GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
