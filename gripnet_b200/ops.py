@@ -295,7 +295,8 @@ class GcnStack(torch.autograd.Function):
         # bias / weight gradients leave the dependency chain dZ -> dY -> dH_{l-1}: side stream (a partitioned
         # run all-reduces them on the caller's stream right away unless the reduction is deferred)
         br = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce)
-        for l in range(n_layers, 0, -1):
+        br_b = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce)   # bias sums: ready before the SpMM,
+        for l in range(n_layers, 0, -1):                                        # never queued behind a weight GEMM
             f, k = dims[l], dims[l - 1]
             h_l, h_prev = outs[l], outs[l - 1]
             if dz_slot is not None:
@@ -311,7 +312,7 @@ class GcnStack(torch.autograd.Function):
                 dz.m, dz.full, dz.dctx = dh, dh, None
             if ctx.has_bias[l - 1] and ctx.needs_input_grad[4 + 2 * (l - 1) + 1]:
                 db = torch.empty(f, dtype=torch.float32, device=dev)
-                with br(dz.m.t):
+                with br_b(dz.m.t):
                     colsum(dz.m, db)
                 grads[2 * (l - 1) + 1] = _reduce(dctx, db)
             dy = M(_new(graph.n_src, f, g))
@@ -340,7 +341,9 @@ class GcnStack(torch.autograd.Function):
                     dz_slot = dprev
                 if l == 1:
                     dx0 = dprev.m.t
-        br.join(deferrable=_only_stored(ctx, dctx))
+        defer = _only_stored(ctx, dctx)
+        br_b.join(deferrable=defer)
+        br.join(deferrable=defer)
         return (dx0, None, None, None) + tuple(grads)
 
 
