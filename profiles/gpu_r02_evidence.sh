@@ -22,22 +22,23 @@ done
 GRIPNET_B200_GEMM=ffma timeout 600 python bench.py --workload pose2 --steps 50 --no-cpu-baseline --no-config5 --no-train-epoch \
   > $out/${tag}_bench_pose2_ffma.json 2> $out/${tag}_bench_pose2_ffma.err
 echo "bench pose2 ffma rc=$?"
-# full captures (one launch of each hot kernel per workload; -s skips the graph-prep and warm-up launches)
-timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'spmm_kernel|pair_walk|distmult_fwd|distmult_grads|tc_gemm_kernel|sgemm_kernel' -s 300 -c 40 -f -o $out/${tag}_full_pose \
+# full captures (one launch of each hot kernel per workload; -s skips the graph-prep and warm-up launches).
+# The .ncu-rep files stay on the box (gpurun returns at most 64 MiB): only their per-launch CSV summaries come back.
+timeout 900 ncu --set full --clock-control none \
+    -k regex:'spmm_kernel|pair_walk|distmult_fwd|distmult_grads|tc_gemm_kernel|tc_tn_kernel|sgemm_kernel' -s 300 -c 30 -f -o /tmp/${tag}_full_pose \
     python bench.py --steps 2 --warmup 1 --eager --no-cpu-baseline --no-config5 --no-train-epoch > $out/${tag}_full_pose.log 2>&1
 echo "ncu full pose rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'tc_gemm_kernel|b_image_kernel|spmm_kernel|pair_walk|sgemm_kernel' -s 150 -c 30 -f -o $out/${tag}_full_pose2 \
+timeout 900 ncu --set full --clock-control none \
+    -k regex:'tc_gemm_kernel|tc_tn_kernel|b_image_kernel|spmm_kernel|pair_walk|distmult_fwd|sgemm_kernel' -s 150 -c 24 -f -o /tmp/${tag}_full_pose2 \
     python bench.py --workload pose2 --steps 1 --warmup 1 --eager --no-cpu-baseline --no-config5 --no-train-epoch > $out/${tag}_full_pose2.log 2>&1
 echo "ncu full pose2 rc=$?"
 for wl in aminer freebase-d; do
-  timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:'spmm_kernel|tc_gemm_kernel|sgemm_kernel' -s 150 -c 24 -f -o $out/${tag}_full_${wl} \
+  timeout 900 ncu --set full --clock-control none \
+      -k regex:'spmm_kernel|tc_gemm_kernel|tc_tn_kernel|sgemm_kernel' -s 150 -c 16 -f -o /tmp/${tag}_full_${wl} \
       python bench.py --workload $wl --steps 1 --warmup 1 --eager --no-cpu-baseline --no-config5 --no-train-epoch > $out/${tag}_full_${wl}.log 2>&1
   echo "ncu full $wl rc=$?"
 done
 for wl in pose pose2 aminer freebase-d; do
-  python profiles/summarize_full.py $out/${tag}_full_${wl}.ncu-rep > $out/${tag}_ncu_full_${wl}.csv 2>/dev/null
+  python profiles/summarize_full.py /tmp/${tag}_full_${wl}.ncu-rep > $out/${tag}_ncu_full_${wl}.csv 2>/dev/null
 done
-ls -la $out | tail -30
+du -sh $out; ls $out | grep ${tag} | head -40
