@@ -50,6 +50,36 @@ __global__ void relu_bwd_kernel(const float* __restrict__ g, int64_t ldg, const 
   dst[r * ldd + c] = (y[r * ldy + c] > 0.f) ? g[r * ldg + c] : 0.f;
 }
 
+// 128-bit variants (F and the leading dimensions multiples of 4, 16-byte aligned bases): one float4 per operand
+__global__ void relu_bwd_vec_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ y, int64_t ldy,
+                                    float* __restrict__ dst, int64_t ldd, int64_t n, int F4) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n * F4) return;
+  const int64_t r = idx / F4;
+  const int c = int(idx - r * F4) * 4;
+  const float4 gv = *reinterpret_cast<const float4*>(g + r * ldg + c);
+  const float4 yv = *reinterpret_cast<const float4*>(y + r * ldy + c);
+  *reinterpret_cast<float4*>(dst + r * ldd + c) = make_float4(yv.x > 0.f ? gv.x : 0.f, yv.y > 0.f ? gv.y : 0.f,
+                                                              yv.z > 0.f ? gv.z : 0.f, yv.w > 0.f ? gv.w : 0.f);
+}
+
+__device__ __forceinline__ float sgn_scaled(float t, float g, float scale) {
+  return g * ((t > 0.f) ? 1.f : ((t < 0.f) ? -1.f : 0.f)) * scale;
+}
+
+__global__ void abs_bwd_vec_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ t, int64_t ldt,
+                                   float* __restrict__ dst, int64_t ldd, int64_t n, int F4, float scale) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n * F4) return;
+  const int64_t r = idx / F4;
+  const int c = int(idx - r * F4) * 4;
+  const float4 gv = *reinterpret_cast<const float4*>(g + r * ldg + c);
+  const float4 tv = *reinterpret_cast<const float4*>(t + r * ldt + c);
+  *reinterpret_cast<float4*>(dst + r * ldd + c) =
+      make_float4(sgn_scaled(tv.x, gv.x, scale), sgn_scaled(tv.y, gv.y, scale), sgn_scaled(tv.z, gv.z, scale),
+                  sgn_scaled(tv.w, gv.w, scale));
+}
+
 __global__ void abs_bwd_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ t, int64_t ldt,
                                float* __restrict__ dst, int64_t ldd, int64_t n, int F, float scale) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -261,6 +291,13 @@ int gn_relu_bwd(const float* g, int64_t ldg, const float* y, int64_t ldy, float*
   if (n < 0 || F <= 0) return GN_ERR_ARG;
   if (n == 0) return GN_OK;
   if (!g || !y || !dst) return GN_ERR_ARG;
+  const bool v4 = F % 4 == 0 && ldg % 4 == 0 && ldy % 4 == 0 && ldd % 4 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  if (v4) {
+    GN_LAUNCH(relu_bwd_vec_kernel, (unsigned)ceil_div(n * (F / 4), 256), 256, 0, as_stream(stream), g, ldg, y, ldy, dst,
+              ldd, n, F / 4);
+    return GN_OK;
+  }
   GN_LAUNCH(relu_bwd_kernel, (unsigned)ceil_div(n * F, 256), 256, 0, as_stream(stream), g, ldg, y, ldy, dst, ldd, n, F);
   return GN_OK;
 }
@@ -270,6 +307,13 @@ int gn_abs_bwd(const float* g, int64_t ldg, const float* t, int64_t ldt, float* 
   if (n < 0 || F <= 0) return GN_ERR_ARG;
   if (n == 0) return GN_OK;
   if (!g || !t || !dst) return GN_ERR_ARG;
+  const bool v4 = F % 4 == 0 && ldg % 4 == 0 && ldt % 4 == 0 && ldd % 4 == 0 &&
+                  ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(t) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  if (v4) {
+    GN_LAUNCH(abs_bwd_vec_kernel, (unsigned)ceil_div(n * (F / 4), 256), 256, 0, as_stream(stream), g, ldg, t, ldt, dst,
+              ldd, n, F / 4, scale);
+    return GN_OK;
+  }
   GN_LAUNCH(abs_bwd_kernel, (unsigned)ceil_div(n * F, 256), 256, 0, as_stream(stream), g, ldg, t, ldt, dst, ldd, n, F,
             scale);
   return GN_OK;
