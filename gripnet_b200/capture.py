@@ -35,6 +35,9 @@ class CapturedStep:
                 out = fn()
                 out[0].backward()
                 post()
+            # static seed of the backward pass: `backward()` alone fills a fresh ones_like(loss) every replay —
+            # one more kernel at the head of the backward's dependency chain
+            self._seed = torch.ones_like(out[0])
         cur.wait_stream(side)
         torch.cuda.synchronize()
         for t in dynamic_inputs:
@@ -44,7 +47,7 @@ class CapturedStep:
         before = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.outputs = fn()
-            self.outputs[0].backward()
+            self.outputs[0].backward(self._seed)
             post()                                     # e.g. the bucketed gradient all-reduce of a partitioned run
         self.launches_per_replay = _lib.launch_count() - before
         torch.cuda.synchronize()

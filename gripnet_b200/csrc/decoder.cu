@@ -355,6 +355,14 @@ __global__ void __launch_bounds__(512) distmult_grads_vec_kernel(const float* __
   if (threadIdx.x == 0) slab_count[rel] = 0;
 }
 
+// arrival counters of the dw reduction: cleared by a KERNEL node — a memset node between two kernels of a captured
+// graph costs several microseconds of dependency latency on the decoder backward's chain
+// (profiles/r02_v15_pose_n1_rank0_summary.txt: 7.5 us between the memset and distmult_grads_vec_kernel)
+__global__ void zero_u32_kernel(unsigned int* __restrict__ p, int n) {
+  const int i = int(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0u;
+}
+
 __global__ void pair_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                  const int64_t* __restrict__ etype, int64_t n_edges, int32_t n_rel,
                                  int32_t* __restrict__ key) {
@@ -581,7 +589,7 @@ int gn_distmult_grads(const float* T, const float* T2, int32_t n_nodes, int32_t 
     if (!ws || ws_bytes < gn_distmult_grads_workspace_bytes(n_nodes, n_rel, D)) return GN_ERR_WORKSPACE;
     count = static_cast<unsigned int*>(ws);
     part = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up(size_t(n_rel) * 4));
-    if (cudaMemsetAsync(count, 0, size_t(n_rel) * 4, st) != cudaSuccess) return GN_ERR_CUDA;
+    GN_LAUNCH(zero_u32_kernel, (unsigned)ceil_div(n_rel, 256), 256, 0, st, count, n_rel);
   }
   if (vec) {
     const int C4 = D / 4;

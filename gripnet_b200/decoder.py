@@ -26,13 +26,15 @@ class multiRelaInnerProductDecoder(Module):
     def forward(self, z, edge_index, edge_type, sigmoid=True):
         return ops.DistMult.apply(z, replicated(self.weight, self.dist_ctx), edge_index, edge_type, bool(sigmoid))
 
-    def score_pair(self, z, pos_edge_index, neg_edge_index, edge_type, sigmoid=True, rel_lo=0, n_rel_local=None):
+    def score_pair(self, z, pos_edge_index, neg_edge_index, edge_type, sigmoid=True, rel_lo=0, n_rel_local=None,
+                   struct_branch=None):
         """``(forward(z, pos, et), forward(z, neg, et))`` of one training step
         (``GripNet-pose.py:133-138``) as one autograd node whose two halves run concurrently.
         ``rel_lo`` / ``n_rel_local``: see ``ops.DistMultPair`` (edge lists that only hold a slice of the relations,
-        ``edge_type`` shifted by ``rel_lo``)."""
+        ``edge_type`` shifted by ``rel_lo``).  ``struct_branch``: a ``streams.Branch`` on which the caller already
+        started the build of the backward's (node, relation) structures; the decoder's backward joins it."""
         return ops.DistMultPair.apply(z, replicated(self.weight, self.dist_ctx), pos_edge_index, neg_edge_index,
-                                      edge_type, bool(sigmoid), int(rel_lo), n_rel_local)
+                                      edge_type, bool(sigmoid), int(rel_lo), n_rel_local, struct_branch)
 
     def reset_parameters(self):
         with torch.no_grad():

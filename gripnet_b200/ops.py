@@ -746,7 +746,8 @@ class DistMultPair(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid, rel_lo=0, n_rel_local=None):
+    def forward(ctx, z, weight, pos_index, neg_index, edge_type, sigmoid, rel_lo=0, n_rel_local=None,
+                struct_branch=None):
         from .graph import pair_struct
         w_full = _as_rows(weight, "weight").contiguous()
         r_loc = w_full.size(0) if n_rel_local is None else int(n_rel_local)
@@ -756,16 +757,23 @@ class DistMultPair(torch.autograd.Function):
         z, w, pi, et = _distmult_check(z, w_loc, pos_index, edge_type)
         _, _, ni, _ = _distmult_check(z, w_loc, neg_index, edge_type)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]      # (grad mode is off inside forward)
-        br, br_s = streams.Branch(), streams.Branch()
+        # the structures are read by the BACKWARD only: their branch (the caller's `struct_branch`, forked earlier in
+        # the step, or the one forked here) is joined at the top of backward(), so the scores never wait for the sort
+        br = streams.Branch()
+        br_s = struct_branch if struct_branch is not None else streams.Branch()
         if need:
             with br_s(pos_index, neg_index, edge_type):
-                pair_struct(neg_index, edge_type, z.size(0), r_loc)
+                pair_struct(neg_index, edge_type, z.size(0), r_loc)      # (cache hits when the caller built them)
                 pair_struct(pos_index, edge_type, z.size(0), r_loc)      # cached after the first step
         with br(z, w, ni, et):
             neg = _distmult_fwd(z, w, ni, et, sigmoid)
         pos = _distmult_fwd(z, w, pi, et, sigmoid)
         br.join()
-        br_s.join()
+        if need and br_s._parent is None:
+            ctx.struct_branch = br_s
+        else:
+            ctx.struct_branch = None
+            br_s.join()
         ctx.sigmoid = bool(sigmoid)
         ctx.keys = (pos_index, neg_index, edge_type)
         ctx.key_versions = tuple(t._version for t in ctx.keys)
@@ -781,6 +789,9 @@ class DistMultPair(torch.autograd.Function):
         _check_versions(ctx.keys, ctx.key_versions, "pos / neg edge_index or edge_type")
         rel_lo, r, r_full = ctx.rel
         n = z.size(0)
+        if ctx.struct_branch is not None:
+            ctx.struct_branch.join()
+            ctx.struct_branch = None
         ps_p = pair_struct(pos_key, et_key, n, r)
         ps_n = pair_struct(neg_key, et_key, n, r)
         g_pos, g_neg = g_pos.contiguous(), g_neg.contiguous()
@@ -799,7 +810,7 @@ class DistMultPair(torch.autograd.Function):
             _lib.check(_lib.load().gn_zero(dw_full.data_ptr(), dw_full.numel() * 4, _stream()), "gn_zero")
             map2d(_lib.EW_COPY, M(dw), M(dw_full[rel_lo: rel_lo + r]))
             dw = dw_full
-        return dz, dw, None, None, None, None, None, None
+        return dz, dw, None, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------

@@ -68,12 +68,13 @@ class PoseModel(Module):
                     G.pair_struct(pos, et, n_dec, self.dmt.num_et if dctx is None else rel_n)
 
         z = self.embed(data, after_first=fork_prep)
-        prep.join()
+        # `prep` is NOT joined here: only the decoder's backward reads the structures (it joins the branch)
         if dctx is None:
-            pos_score, neg_score = self.dmt.score_pair(z, pos, neg, et)
+            pos_score, neg_score = self.dmt.score_pair(z, pos, neg, et, struct_branch=prep)
             return link_prediction_loss(pos_score, neg_score), z, pos_score, neg_score
         z_full = parallel.all_gather_rows(z, dctx, data["n_d_global"])
-        pos_score, neg_score = self.dmt.score_pair(z_full, pos, neg, et, rel_lo=rel_lo, n_rel_local=rel_n)
+        pos_score, neg_score = self.dmt.score_pair(z_full, pos, neg, et, rel_lo=rel_lo, n_rel_local=rel_n,
+                                                   struct_branch=prep)
         loss = parallel.global_mean_loss(link_prediction_loss(pos_score, neg_score), pos_score.numel(),
                                          data["e_dd_global"], dctx)
         return loss, z, pos_score, neg_score

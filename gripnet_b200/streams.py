@@ -133,6 +133,15 @@ class Branch:
             self._parent._keep.extend(self._keep)
         self._keep.clear()
 
+    def __del__(self):
+        # a branch handed to a consumer that never ran (e.g. the structure branch of a decoder whose backward was
+        # never called): order the caller's stream behind the side work BEFORE the held temporaries are released
+        try:
+            if self.enabled and self._dirty:
+                self._join_now()
+        except Exception:          # interpreter / CUDA context shutting down
+            pass
+
 
 # ---- joins deferred to the end of the autograd backward pass -------------------------------------------------
 _deferred = []
