@@ -81,6 +81,8 @@ SIGNATURES = {
     "gn_tc_gemm": (_INT, [_INT, _I32, _I32, _I32, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _SZ, _P]),
     "gn_tc_gemm_rel_workspace_bytes": (_SZ, [_I32, _I32, _I32, _I32]),
     "gn_tc_gemm_rel": (_INT, [_I32, _I32, _I32, _I32, _P, _I64, _P, _P, _I64, _P, _SZ, _P]),
+    "gn_tc_rel_image": (_INT, [_I32, _I32, _I32, _I32, _P, _P, _SZ, _P]),
+    "gn_tc_gemm_rel_image": (_INT, [_I32, _I32, _I32, _I32, _P, _I64, _P, _SZ, _P, _I64, _P]),
     "gn_tc_tn_workspace_bytes": (_SZ, [_I64, _I32, _I32]),
     "gn_tc_tn": (_INT, [_P, _I64, _P, _I64, _I64, _I32, _I32, _P, _I64, _I32, _I64, _P, _SZ, _P]),
     "gn_distmult_fwd": (_INT, [_P, _I64, _I32, _P, _P, _P, _P, _I64, _INT, _P, _P]),

@@ -12,7 +12,7 @@ rebuilt by the captured K1 kernels on every replay.
 """
 import torch
 
-from . import _lib
+from . import _lib, streams
 
 
 class CapturedStep:
@@ -27,7 +27,9 @@ class CapturedStep:
         self.params = [p for p in parameters]
         post = post_backward if post_backward is not None else (lambda: None)
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        # warm-up and capture run on ONE high-priority stream: the chain's kernels keep that priority in the graph,
+        # the background branches (streams.Branch(background=True)) stay below it
+        side = torch.cuda.Stream(priority=streams.chain_priority())
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(max(int(warmup), 1)):      # builds and caches every static graph structure
@@ -45,7 +47,7 @@ class CapturedStep:
         self._drop_grads()                             # are (re)built INSIDE the graph, not served from cache
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=side):
             self.outputs = fn()
             self.outputs[0].backward(self._seed)
             post()                                     # e.g. the bucketed gradient all-reduce of a partitioned run

@@ -44,6 +44,99 @@ __global__ void __launch_bounds__(256) distmult_fwd_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------
+// forward, batch form (D % 4 == 0, D <= 128): a warp takes 32 consecutive edges per step of its loop.
+//  * the three index arrays are read ONCE per edge with coalesced loads (lane l = edge l of the batch) and handed to
+//    the feature lanes with shuffles — the per-edge form above reads them once per feature lane and spends most of
+//    its issue slots on index / address arithmetic (ncu r02_v17: 28 warp instructions per edge, 7 needed);
+//  * 8 feature lanes per edge: one 128-byte piece of an embedding row per quarter-warp, the unit the L1 serves per
+//    wavefront (4 lanes x 16 B touch two rows per wavefront and move 64 B);
+//  * edge lists are relation-major in every pose pipeline (GripNet-pose.py:59-70 builds them from `range_list`), so
+//    the 32 edges of a batch normally share one relation: its weight row then lives in registers for the batch and
+//    one third of the row gathers disappears.  Mixed batches fetch the row per edge.
+// Summation order per edge: feature lane fl adds its vectors v = 0..NV-1 in order, then the fixed 8-lane tree.
+// ---------------------------------------------------------------------------
+// row `i` of a table whose rows are `ld_bytes` apart, as ONE 32x32 -> 64-bit multiply-add (IMAD.WIDE.U32)
+__device__ __forceinline__ const float4* row_ptr(const float4* base, int i, unsigned ld_bytes) {
+  return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(base) +
+                                         static_cast<unsigned long long>(static_cast<unsigned>(i)) * ld_bytes);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, NV <= 3 ? 4 : 3) distmult_fwd_batch_kernel(const float* __restrict__ z, int64_t ldz, int D,
+                                                                    const float* __restrict__ w,
+                                                                    const int64_t* __restrict__ src,
+                                                                    const int64_t* __restrict__ dst,
+                                                                    const int64_t* __restrict__ etype,
+                                                                    int64_t n_edges, int sigmoid,
+                                                                    float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int slot = lane >> 3, fl = lane & 7;
+  const int D4 = D >> 2;
+  const unsigned ldb = unsigned(ldz) * 4u, wdb = unsigned(D) * 4u;
+  const float4* __restrict__ z4 = reinterpret_cast<const float4*>(z) + fl;
+  const float4* __restrict__ w4 = reinterpret_cast<const float4*>(w) + fl;
+  bool ok[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) ok[v] = (v * 8 + fl) < D4;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  const int64_t n_batches = (n_edges + 31) >> 5;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t b = warp; b < n_batches; b += n_warps) {
+    const int64_t e = (b << 5) + lane;
+    const bool live = e < n_edges;
+    int s = 0, d = 0, r;
+    const int r_first = int(__ldg(etype + (b << 5)));
+    r = r_first;
+    if (live) {
+      s = int(__ldg(src + e));
+      d = int(__ldg(dst + e));
+      r = int(__ldg(etype + e));
+    }
+    const bool uniform = __all_sync(kFull, r == r_first);
+    float4 wv[NV];
+    if (uniform) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) wv[v] = ok[v] ? __ldg(row_ptr(w4, r_first, wdb) + v * 8) : zero;
+    }
+    float mine = 0.f;
+#pragma unroll 2
+    for (int t = 0; t < 8; ++t) {
+      const int from = t * 4 + slot;
+      const int ss = __shfl_sync(kFull, s, from), dd = __shfl_sync(kFull, d, from);
+      const float4* za = row_ptr(z4, ss, ldb);
+      const float4* zb = row_ptr(z4, dd, ldb);
+      float4 a[NV], c[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        a[v] = ok[v] ? __ldg(za + v * 8) : zero;
+        c[v] = ok[v] ? __ldg(zb + v * 8) : zero;
+      }
+      if (!uniform) {
+        const int rr = __shfl_sync(kFull, r, from);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) wv[v] = ok[v] ? __ldg(row_ptr(w4, rr, wdb) + v * 8) : zero;
+      }
+      float acc = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        acc = fmaf(a[v].x * c[v].x, wv[v].x, acc);
+        acc = fmaf(a[v].y * c[v].y, wv[v].y, acc);
+        acc = fmaf(a[v].z * c[v].z, wv[v].z, acc);
+        acc = fmaf(a[v].w * c[v].w, wv[v].w, acc);
+      }
+      acc += __shfl_xor_sync(kFull, acc, 4);
+      acc += __shfl_xor_sync(kFull, acc, 2);
+      acc += __shfl_xor_sync(kFull, acc, 1);
+      // edge L of the batch was scored at step L / 4 by the lane group L % 4
+      const float got = __shfl_sync(kFull, acc, (lane & 3) << 3);
+      if ((lane >> 2) == t) mine = got;
+    }
+    if (live) out[e] = sigmoid ? 1.0f / (1.0f + expf(-mine)) : mine;
+  }
+}
+
 __global__ void distmult_coef_kernel(const float* __restrict__ grad_out, const float* __restrict__ out, int64_t n,
                                      int sigmoid, float* __restrict__ coef) {
   const int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -116,6 +209,65 @@ __global__ void __launch_bounds__(256) pair_walk_kernel(const gn_csr csr, const 
   const int row = ci.row;
   auto emit = [&](int, int f, const Vec<VEC>& sum) { store_vec<VEC>(T + int64_t(row) * D + f, sum); };
   finish_row<LPE, VEC, NV>(csr, ci, acc, D, partial, emit);
+}
+
+// Batch form of the walk (D % 4 == 0, D <= 128): like spmm_kernel, a warp reads 32 entries (other endpoint, coef of
+// the entry's edge) with one coalesced load + one gather per lane, then hands them to 4 entry slots x 8 feature lanes
+// with shuffles: no dependent index -> row round trip per step, a third of the instructions of the form above
+// (ncu r02_v17: 11 warp instructions per entry), 128-byte row pieces per quarter-warp.  Same row-split finish.
+template <int NV>
+__global__ void __launch_bounds__(256, 4) pair_walk_batch_kernel(const gn_csr csr, const int32_t* __restrict__ ent_other,
+                                                                 const int32_t* __restrict__ ent_eid,
+                                                                 const float* __restrict__ coef,
+                                                                 const float* __restrict__ z, int64_t ldz, int D,
+                                                                 float* __restrict__ T, float* __restrict__ partial) {
+  ChunkInfo ci;
+  if (!chunk_info(csr, ci)) return;
+  const int lane = threadIdx.x & 31;
+  const int slot = lane >> 3, fl = lane & 7;
+  const int D4 = D >> 2;
+  const unsigned ldb = unsigned(ldz) * 4u;
+  const float4* __restrict__ z4 = reinterpret_cast<const float4*>(z) + fl;
+  bool ok[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) ok[v] = (v * 8 + fl) < D4;
+  Vec<4> acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[v].v[i] = 0.f;
+  for (int base = ci.beg; base < ci.end; base += 32) {
+    const int mine = base + lane;
+    int o = 0;            // entries past the end of the chunk: row 0 with coefficient 0
+    float g = 0.f;
+    if (mine < ci.end) {
+      o = __ldg(ent_other + mine);
+      g = __ldg(coef + __ldg(ent_eid + mine));
+    }
+    const int steps = min(8, (ci.end - base + 3) >> 2);
+#pragma unroll 2
+    for (int t = 0; t < steps; ++t) {
+      const int from = t * 4 + slot;
+      const int oo = __shfl_sync(kFull, o, from);
+      const float gg = __shfl_sync(kFull, g, from);
+      const float4* za = row_ptr(z4, oo, ldb);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (ok[v]) {
+          const float4 a = __ldg(za + v * 8);
+          acc[v].v[0] = fmaf(gg, a.x, acc[v].v[0]);
+          acc[v].v[1] = fmaf(gg, a.y, acc[v].v[1]);
+          acc[v].v[2] = fmaf(gg, a.z, acc[v].v[2]);
+          acc[v].v[3] = fmaf(gg, a.w, acc[v].v[3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) reduce_slots<8, 4>(acc[v]);
+  const int row = ci.row;
+  auto emit = [&](int, int f, const Vec<4>& sum) { store_vec<4>(T + int64_t(row) * D + f, sum); };
+  finish_row<8, 4, NV>(csr, ci, acc, D, partial, emit);
 }
 
 // dz / dw from T (and an optional second T of another edge list).
@@ -440,6 +592,12 @@ inline WidthPlan plan_width(int D, bool can_vec4, bool wide = false) {
   return p;
 }
 
+// GRIPNET_B200_DECODER_KERNELS=legacy keeps the per-edge / per-entry forms (A/B measurements, parity tests of both)
+static bool legacy_decoder_kernels() {
+  const char* e = std::getenv("GRIPNET_B200_DECODER_KERNELS");
+  return e && e[0] == 'l';
+}
+
 }  // namespace gn
 
 using namespace gn;
@@ -453,6 +611,23 @@ int gn_distmult_fwd(const float* z, int64_t ldz, int32_t D, const float* w, cons
   if (!z || !w || !src || !dst || !etype || !out) return GN_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   const bool v4 = (D % 4 == 0) && (ldz % 4 == 0) && aligned16(z) && aligned16(w);
+  if (v4 && D <= 128 && ldz < (int64_t(1) << 30) && !legacy_decoder_kernels()) {
+    const int nv = (D / 4 + 7) / 8;
+    int64_t nwarps = ceil_div(n_edges, 32);
+    const int64_t cap = int64_t(148) * 4 * 8 * 2;            // two batches per resident warp before the loop pays off
+    if (nwarps > cap) nwarps = cap;
+    const unsigned g = (unsigned)ceil_div(nwarps, 8);
+#define GN_FWDB_CASE(N)                                                                                              \
+  if (nv == N) {                                                                                                     \
+    GN_LAUNCH((distmult_fwd_batch_kernel<N>), g, 256, 0, st, z, ldz, D, w, src, dst, etype, n_edges, sigmoid, out);  \
+    return GN_OK;                                                                                                    \
+  }
+    GN_FWDB_CASE(1)
+    GN_FWDB_CASE(2)
+    GN_FWDB_CASE(3)
+    GN_FWDB_CASE(4)
+#undef GN_FWDB_CASE
+  }
   const int units = v4 ? D / 4 : D;
   const int lpe = units <= 32 ? 4 : (units <= 64 ? 8 : 32);
   const int epi = 32 / lpe;
@@ -547,6 +722,20 @@ int gn_distmult_bwd_pairs(const gn_csr* pair_csr, const int32_t* ent_other, cons
   if (!p.ok) return GN_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   const unsigned grid = (unsigned)ceil_div(csr.n_chunks, 8);
+  if (v4 && D <= 128 && ldz < (int64_t(1) << 30) && !legacy_decoder_kernels()) {
+    const int nv = (D / 4 + 7) / 8;
+#define GN_PWB_CASE(N)                                                                                        \
+  if (nv == N) {                                                                                              \
+    GN_LAUNCH((pair_walk_batch_kernel<N>), grid, 256, 0, st, csr, ent_other, ent_eid, coef, z, ldz, D, T,     \
+              partial);                                                                                       \
+    return GN_OK;                                                                                             \
+  }
+    GN_PWB_CASE(1)
+    GN_PWB_CASE(2)
+    GN_PWB_CASE(3)
+    GN_PWB_CASE(4)
+#undef GN_PWB_CASE
+  }
 #define GN_PW_CASE(L, V, N)                                                                                  \
   if (p.lpe == L && p.vec == V && p.nv == N) {                                                               \
     GN_LAUNCH((pair_walk_kernel<L, V, N>), grid, 256, 0, st, csr, ent_other, ent_eid, coef, z, ldz, D, T,    \

@@ -242,18 +242,26 @@ __global__ void __launch_bounds__(1024) chunk_one_block_kernel(const int32_t* __
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
+  constexpr int kItems = 4;                         // consecutive rows per thread: a third of the block-wide scans
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < n_rows; base += 1024) {
-    const int r = base + threadIdx.x;
-    int c = 0, beg = 0;
-    if (r < n_rows) {
-      beg = rowptr[r];
-      const int len = rowptr[r + 1] - beg;
-      c = (len + chunk_len - 1) / chunk_len;
-      if (c < 1) c = 1;
-      if (row_counter) row_counter[r] = 0;
+  for (int base = 0; base < n_rows; base += 1024 * kItems) {
+    const int r0 = base + int(threadIdx.x) * kItems;
+    int ptr[kItems + 1];
+#pragma unroll
+    for (int i = 0; i <= kItems; ++i) ptr[i] = (r0 + i <= n_rows) ? rowptr[r0 + i] : 0;
+    int c[kItems], tsum = 0;
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      c[i] = 0;
+      if (r0 + i < n_rows) {
+        const int len = ptr[i + 1] - ptr[i];
+        c[i] = (len + chunk_len - 1) / chunk_len;
+        if (c[i] < 1) c[i] = 1;
+        if (row_counter) row_counter[r0 + i] = 0;
+      }
+      tsum += c[i];
     }
-    int incl = c;
+    int incl = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(kFull, incl, o);
@@ -272,18 +280,22 @@ __global__ void __launch_bounds__(1024) chunk_one_block_kernel(const int32_t* __
       warp_sums[lane] = wi - w;
     }
     __syncthreads();
-    const int c0 = carry + warp_sums[warp] + incl - c;
-    if (r < n_rows) {
-      chunk_ptr[r] = c0;
-      for (int k = 0; k < c; ++k) {
-        if (c0 + k < capacity) {
-          chunk_row[c0 + k] = r;
-          chunk_beg[c0 + k] = beg + k * chunk_len;
+    int c0 = carry + warp_sums[warp] + incl - tsum;
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+      if (r0 + i < n_rows) {
+        chunk_ptr[r0 + i] = c0;
+        for (int k = 0; k < c[i]; ++k) {
+          if (c0 + k < capacity) {
+            chunk_row[c0 + k] = r0 + i;
+            chunk_beg[c0 + k] = ptr[i] + k * chunk_len;
+          }
         }
+        c0 += c[i];
       }
     }
     __syncthreads();
-    if (threadIdx.x == 1023) carry = c0 + c;
+    if (threadIdx.x == 1023) carry = c0;            // rows beyond n_rows add nothing: the last thread ends the tile
     __syncthreads();
   }
   if (threadIdx.x == 0) chunk_ptr[n_rows] = carry;

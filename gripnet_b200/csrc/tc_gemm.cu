@@ -528,9 +528,29 @@ extern "C" size_t gn_tc_gemm_rel_workspace_bytes(int32_t M, int32_t n_rel, int32
   return pl.ok ? align_up(pl.image_bytes) : 0;
 }
 
-extern "C" int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
-                              const float* W, float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream) {
-  if (M < 0 || n_rel <= 0 || f <= 0 || K <= 0 || !X || !W || !Y) return GN_ERR_ARG;
+// The image of W_flat depends on the weights only: gn_tc_rel_image builds it (e.g. at the top of a training step, off
+// the dependency chain), gn_tc_gemm_rel_image runs the product with a prepared image, gn_tc_gemm_rel does both.
+extern "C" int gn_tc_rel_image(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* W, void* ws,
+                               size_t ws_bytes, void* stream) {
+  if (M < 0 || n_rel <= 0 || f <= 0 || K <= 0 || !W) return GN_ERR_ARG;
+  if (M == 0) return GN_OK;
+  const int64_t N64 = int64_t(n_rel) * f;
+  if (N64 >= (int64_t(1) << 31)) return GN_ERR_RANGE;
+  const int N = int(N64);
+  if (K % 4 != 0) return GN_ERR_ARG;
+  const tc::Plan pl = tc::make_plan(M, N, K, rel_nt_cap(M, N));
+  if (!pl.ok) return GN_ERR_ARG;
+  if (!ws || ws_bytes < pl.image_bytes || (reinterpret_cast<uintptr_t>(ws) & 15u) != 0) return GN_ERR_WORKSPACE;
+  const int64_t total = int64_t(pl.n_tiles) * pl.n_kb * tc::CHUNKS * pl.nt;
+  const tc::BView bv{W, int64_t(f), int64_t(K) * f, 2, f};
+  GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, as_stream(stream), bv, K, N, pl.nt, pl.n_kb,
+            static_cast<char*>(ws));
+  return GN_OK;
+}
+
+extern "C" int gn_tc_gemm_rel_image(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
+                                    const void* image, size_t image_bytes, float* Y, int64_t ldy, void* stream) {
+  if (M < 0 || n_rel <= 0 || f <= 0 || K <= 0 || !X || !Y) return GN_ERR_ARG;
   if (M == 0) return GN_OK;
   const int64_t N64 = int64_t(n_rel) * f;
   if (N64 >= (int64_t(1) << 31)) return GN_ERR_RANGE;
@@ -539,22 +559,24 @@ extern "C" int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, co
   if (!al16(X) || ldx % 4 != 0 || K % 4 != 0 || !al16(Y) || ldy % 4 != 0) return GN_ERR_ARG;
   const tc::Plan pl = tc::make_plan(M, N, K, rel_nt_cap(M, N));
   if (!pl.ok) return GN_ERR_ARG;
-  if (!ws || ws_bytes < pl.image_bytes || !al16(ws)) return GN_ERR_WORKSPACE;
-  cudaStream_t st = as_stream(stream);
-  const int64_t total = int64_t(pl.n_tiles) * pl.n_kb * tc::CHUNKS * pl.nt;
-  const tc::BView bv{W, int64_t(f), int64_t(K) * f, 2, f};
-  GN_LAUNCH(tc::b_image_kernel, (unsigned)ceil_div(total, 256), 256, 0, st, bv, K, N, pl.nt, pl.n_kb,
-            static_cast<char*>(ws));
+  if (!image || image_bytes < pl.image_bytes || !al16(image)) return GN_ERR_WORKSPACE;
   tc::Params p;
   p.M = M; p.N = N; p.K = K;
   p.A = X; p.lda = ldx; p.C = Y; p.ldc = ldy;
   p.addend = nullptr; p.ldd = 0; p.mask = nullptr; p.ldm = 0;
-  p.b_image = static_cast<const char*>(ws);
-  p.B = W; p.ldb = f; p.transB = 0;
+  p.b_image = static_cast<const char*>(image);
+  p.B = nullptr; p.ldb = f; p.transB = 0;
   p.nt = pl.nt; p.n_kb = pl.n_kb; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
   p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc; p.b_resident = pl.b_resident;
   GN_CHECK(tc_set_smem_attr());
   dim3 grid(tc_grid_x(M, pl), (unsigned)pl.n_tiles);
-  GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
+  GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, as_stream(stream), p);
   return GN_OK;
+}
+
+extern "C" int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
+                              const float* W, float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream) {
+  if (!X || !W || !Y) return GN_ERR_ARG;
+  GN_CHECK(gn_tc_rel_image(M, n_rel, f, K, W, ws, ws_bytes, stream));
+  return gn_tc_gemm_rel_image(M, n_rel, f, K, X, ldx, ws, ws_bytes, Y, ldy, stream);
 }

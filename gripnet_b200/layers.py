@@ -190,6 +190,15 @@ class homoGraph(Module):
         with torch.no_grad():
             self.embedding.normal_()                                  # layers.py:249-250
 
+    def prologue(self, n_rows):
+        """Start everything of the next ``forward`` that depends on the parameters only (the relational layers'
+        ``W[r]`` and their tensor-core operand images for an ``n_rows``-row input) on a background stream.  Optional:
+        a training step calls it before its first kernel; ``forward`` picks the results up (``ops.RelPrologue``)."""
+        convs = list(self.conv_list)
+        if self.multi_relational and all(type(c) is myRGCN for c in convs):
+            return ops.RelPrologue([(c.basis, c.att) for c in convs], int(n_rows))
+        return None
+
     def forward(self, x, homo_edge_index, edge_weight=None, edge_type=None, range_list=None, if_catout=False):
         if self.start_graph:
             x = self.embedding                                        # the input x is ignored, layers.py:261-262

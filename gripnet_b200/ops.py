@@ -151,13 +151,22 @@ def sgemm(ta, tb, m, n, k, a_ptr, lda, b_ptr, ldb, c_ptr, ldc, device, batch=1, 
 
 # relation transform Y[:, r, :] = X W[r]: tensor cores whenever the 3xTF32 kernel's alignment rules hold
 # ("ffma" keeps it on the CUDA cores — the A/B switch of the config-4 measurements)
-def rel_transform(x, w, y, r, k, f, device):
-    """``x``: M view [n, k]; ``w``: contiguous [r, k, f] tensor; ``y``: M view [n, r*f]."""
+def _rel_tc_ok(k, ldx, ldy, x_ptr, y_ptr):
+    return GEMM_PATH != "ffma" and k % 4 == 0 and ldx % 4 == 0 and ldy % 4 == 0 and x_ptr % 16 == 0 and y_ptr % 16 == 0
+
+
+def rel_transform(x, w, y, r, k, f, device, image=None):
+    """``x``: M view [n, k]; ``w``: contiguous [r, k, f] tensor; ``y``: M view [n, r*f].  ``image``: the tensor-core
+    operand image of ``w`` for ``n`` rows when a ``RelPrologue`` already built it."""
     lib = _lib.load()
     n = x.n
     if n == 0:
         return
-    if GEMM_PATH != "ffma" and k % 4 == 0 and x.ld % 4 == 0 and y.ld % 4 == 0 and x.ptr % 16 == 0 and y.ptr % 16 == 0:
+    if _rel_tc_ok(k, x.ld, y.ld, x.ptr, y.ptr):
+        if image is not None:
+            _lib.check(lib.gn_tc_gemm_rel_image(n, r, f, k, x.ptr, x.ld, _ptr(image), image.numel(), y.ptr, y.ld,
+                                                _stream()), "gn_tc_gemm_rel_image")
+            return
         nbytes = int(lib.gn_tc_gemm_rel_workspace_bytes(n, r, f, k))
         if nbytes:
             img = _ws(nbytes, device)
@@ -165,6 +174,63 @@ def rel_transform(x, w, y, r, k, f, device):
                                           _stream()), "gn_tc_gemm_rel")
             return
     sgemm(False, False, n, f, k, x.ptr, x.ld, w.data_ptr(), f, y.ptr, y.ld, device, batch=r, sa=0, sb=k * f, sc=f)
+
+
+def rel_weights(basis, att):
+    """``W[r] = sum_b att[r, b] basis[b]`` (``layers.py:172-173``) as a contiguous [r, k, f] tensor."""
+    nb, k, f = basis.shape
+    r = att.size(0)
+    bs, at = basis.contiguous(), att.contiguous()
+    w = torch.empty((r, k, f), dtype=torch.float32, device=basis.device)
+    sgemm(False, False, r, k * f, nb, at.data_ptr(), nb, bs.data_ptr(), k * f, w.data_ptr(), k * f, basis.device)
+    return w
+
+
+class RelPrologue:
+    """Everything of an RGCN stack's forward that depends on the PARAMETERS only — ``W[r]`` of every layer and its
+    tensor-core operand image for ``n_rows`` input rows — launched on a background branch.  A training step creates it
+    before its first kernel (``homoGraph.prologue``), so these launches are roots of the captured graph instead of
+    sitting on the dependency chain between the previous supervertex and the relational layer.  ``RgcnStack.forward``
+    picks the entries up by parameter identity + version and joins the branch."""
+
+    _pending = {}
+
+    def __init__(self, layers, n_rows):
+        """``layers``: [(basis, att), ...] parameters of the stack."""
+        lib = _lib.load()
+        self.branch = streams.Branch(background=True)
+        self.entries = []
+        flat = [t for pair in layers for t in pair]
+        with self.branch(*flat):
+            for basis, att in layers:
+                w = rel_weights(basis.detach(), att.detach())
+                nb, k, f = basis.shape
+                r = att.size(0)
+                image = None
+                nbytes = int(lib.gn_tc_gemm_rel_workspace_bytes(n_rows, r, f, k)) if GEMM_PATH != "ffma" and k % 4 == 0 else 0
+                if nbytes and n_rows > 0:
+                    image = _ws(nbytes, basis.device)
+                    _lib.check(lib.gn_tc_rel_image(n_rows, r, f, k, w.data_ptr(), _ptr(image), nbytes, _stream()),
+                               "gn_tc_rel_image")
+                key = (basis.data_ptr(), att.data_ptr())
+                entry = (self.branch, basis._version, att._version, int(n_rows), w, image)
+                RelPrologue._pending.pop(key, None)
+                RelPrologue._pending[key] = entry
+                self.entries.append(key)
+        while len(RelPrologue._pending) > 16:               # entries nobody took (their branch joins when dropped)
+            RelPrologue._pending.pop(next(iter(RelPrologue._pending)))
+
+    @staticmethod
+    def take(basis, att, n_rows):
+        """``(w, image)`` prepared for these parameters (branch joined), or None."""
+        e = RelPrologue._pending.pop((basis.data_ptr(), att.data_ptr()), None)
+        if e is None:
+            return None
+        branch, vb, va, rows, w, image = e
+        branch.join()
+        if vb != basis._version or va != att._version:
+            return None                                  # parameters changed since the prologue: recompute
+        return w, (image if rows == int(n_rows) else None)
 
 
 # weight gradients C = A^T B (reduction over the node rows): tensor cores when the reduction is long enough to be a
@@ -294,8 +360,8 @@ class GcnStack(torch.autograd.Function):
         dx0 = None
         # bias / weight gradients leave the dependency chain dZ -> dY -> dH_{l-1}: side stream (a partitioned
         # run all-reduces them on the caller's stream right away unless the reduction is deferred)
-        br = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce)
-        br_b = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce)   # bias sums: ready before the SpMM,
+        br = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce, background=True)
+        br_b = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce, background=True)   # bias sums: ready before the SpMM,
         for l in range(n_layers, 0, -1):                                        # never queued behind a weight GEMM
             f, k = dims[l], dims[l - 1]
             h_l, h_prev = outs[l], outs[l - 1]
@@ -393,9 +459,10 @@ class RgcnStack(torch.autograd.Function):
             if att[l].size(0) != r:
                 raise RuntimeError("att rows must equal the number of relations of the graph")
             bs, at, rt = basis[l].contiguous(), att[l].contiguous(), root[l].contiguous()
-            # W[r] = sum_b att[r,b] basis[b]   (layers.py:172-173)
-            w = torch.empty((r, k, f), dtype=torch.float32, device=dev)
-            sgemm(False, False, r, k * f, nb, at.data_ptr(), nb, bs.data_ptr(), k * f, w.data_ptr(), k * f, dev)
+            n_in = n if dctx is None else dctx.world * blk           # rows of the (gathered) layer input
+            # W[r] = sum_b att[r,b] basis[b]   (layers.py:172-173) — from the step's prologue when there is one
+            pre = RelPrologue.take(basis[l], att[l], n_in)
+            w, image = pre if pre is not None else (rel_weights(bs, at), None)
             xin = M(x0) if l == 0 else outs[l]
             hl = M(buf, offs[l + 1], f) if catout else M(_new(n, f, x0))
             # root term X root (layers.py:193), next to the relation transforms; the segmented mean
@@ -412,7 +479,7 @@ class RgcnStack(torch.autograd.Function):
             else:
                 xall = xin
             yfull = _new(xall.n, r * f, x0)
-            rel_transform(xall, w, M(yfull), r, k, f, dev)
+            rel_transform(xall, w, M(yfull), r, k, f, dev, image=image if xall.n == n_in else None)
             b = bias[l].contiguous() if bias[l] is not None else None
             br.join()
             spmm(graph.fwd, M(yfull.view(yfull.size(0) * r, f)), hl, f, row_scale=graph.inv_cnt, bias=b, addend=hl,
@@ -456,7 +523,7 @@ class RgcnStack(torch.autograd.Function):
         grads = [None] * (4 * n_layers)
         dz_slot = None
         dx0 = None
-        br = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce)   # parameter gradients off the chain
+        br = streams.Branch(enabled=dctx is None or dctx.defer_grad_reduce, background=True)   # parameter gradients off the chain
         for l in range(n_layers, 0, -1):
             f, k = dims[l], dims[l - 1]
             w, bs, at, rt = ws_list[l - 1]
@@ -760,7 +827,7 @@ class DistMultPair(torch.autograd.Function):
         # the structures are read by the BACKWARD only: their branch (the caller's `struct_branch`, forked earlier in
         # the step, or the one forked here) is joined at the top of backward(), so the scores never wait for the sort
         br = streams.Branch()
-        br_s = struct_branch if struct_branch is not None else streams.Branch()
+        br_s = struct_branch if struct_branch is not None else streams.Branch(background=True)
         if need:
             with br_s(pos_index, neg_index, edge_type):
                 pair_struct(neg_index, edge_type, z.size(0), r_loc)      # (cache hits when the caller built them)

@@ -7,6 +7,8 @@ forward/loss part of its ``train()`` (``:117-142``); ``AminerModel`` =
 a ``state_dict`` saved by the reference scripts loads unchanged.
 Used by ``bench.py``, ``__graft_entry__.smoke()`` and the parity tests.
 """
+import os
+
 import torch
 from torch.nn import Module, Parameter
 
@@ -16,6 +18,10 @@ from . import graph as G
 from . import ops, streams
 from .layers import homoGraph, interGraph
 from .losses import link_prediction_loss, node_classification_loss
+
+
+PROLOGUE = os.environ.get("GRIPNET_B200_PROLOGUE", "1") != "0"
+PREP_AT = os.environ.get("GRIPNET_B200_PREP_AT", "top")
 
 
 class PoseModel(Module):
@@ -56,18 +62,26 @@ class PoseModel(Module):
             n_dec = dctx.world * dctx.block(data["n_d_global"])
             rel_lo, rel_n = data["dd_rel_lo"], data["dd_rel_n"]
         # the decoder backward's (node, relation) structures depend on the edge lists only — the negatives' one is
-        # rebuilt every step (GripNet-pose.py:131 resamples them): it runs on a side stream next to the embedding
-        # pass instead of the decoder waiting for it.  It is forked right AFTER the first supervertex has been
-        # enqueued: the step's dependency chain is then the first root of the captured graph and starts at once
-        prep = streams.Branch()
+        # rebuilt every step (GripNet-pose.py:131 resamples them) — and the relational layer's W[r] / tensor-core
+        # image on the parameters only.  Both are forked BEFORE the first kernel of the step, on background-priority
+        # streams: they are roots of the captured graph, fill SM slots the dependency chain leaves idle, and are
+        # joined where they are consumed (the decoder's backward; RgcnStack.forward).  PREP_AT = "first" forks them
+        # behind the first supervertex instead (the chain alone starts the step; they then end ~100 us later).
+        prep = streams.Branch(background=PREP_AT == "top")
 
         def fork_prep():
+            if PROLOGUE:
+                self.dd.prologue(n_dec)
             if torch.is_grad_enabled():
                 with prep(pos, neg, et):
                     G.pair_struct(neg, et, n_dec, self.dmt.num_et if dctx is None else rel_n)
                     G.pair_struct(pos, et, n_dec, self.dmt.num_et if dctx is None else rel_n)
 
-        z = self.embed(data, after_first=fork_prep)
+        if PREP_AT == "top":
+            fork_prep()
+            z = self.embed(data)
+        else:
+            z = self.embed(data, after_first=fork_prep)
         # `prep` is NOT joined here: only the decoder's backward reads the structures (it joins the branch)
         if dctx is None:
             pos_score, neg_score = self.dmt.score_pair(z, pos, neg, et, struct_branch=prep)

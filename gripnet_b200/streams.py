@@ -33,6 +33,11 @@ ENABLED = os.environ.get("GRIPNET_B200_STREAMS", "1") != "0"
 # parameter-gradient branches may stay un-joined until the END of the autograd backward pass (see
 # ``Branch.join(deferrable=True)``); "0" joins every branch where it was forked
 DEFER_JOINS = os.environ.get("GRIPNET_B200_DEFER_JOINS", "1") != "0"
+# Stream priorities: the kernels of the step's dependency chain (and the branches that are joined straight back into
+# it) run on high-priority streams, parameter-gradient / structure-build branches ("background") on default-priority
+# ones, so a chain kernel that becomes ready while a wide weight-gradient kernel is in flight gets the next free SM
+# slots.  A captured graph keeps the priority of the stream each kernel was captured on.  "0" = one priority.
+PRIORITIES = os.environ.get("GRIPNET_B200_PRIORITIES", "1") != "0"
 _N_SIDE = 8
 _tls = threading.local()
 _pools = {}
@@ -56,12 +61,17 @@ def keep(*tensors):
         b._keep.extend(t for t in tensors if t is not None)
 
 
-def _next_side(device, avoid=None):
+def chain_priority():
+    return -1 if PRIORITIES else 0
+
+
+def _next_side(device, avoid=None, background=False):
     idx = device.index if device.index is not None else torch.cuda.current_device()
+    prio = 0 if background else chain_priority()
     with _pool_lock:
-        pool = _pools.get(idx)
+        pool = _pools.get((idx, prio))
         if pool is None:
-            pool = _pools[idx] = [[torch.cuda.Stream(device=idx) for _ in range(_N_SIDE)], 0]
+            pool = _pools[(idx, prio)] = [[torch.cuda.Stream(device=idx, priority=prio) for _ in range(_N_SIDE)], 0]
         for _ in range(_N_SIDE):
             pool[1] = (pool[1] + 1) % _N_SIDE
             if avoid is None or pool[0][pool[1]].cuda_stream != avoid.cuda_stream:
@@ -80,7 +90,9 @@ class Branch:
         br.join()                               # before `out` is consumed / returned
     """
 
-    def __init__(self, enabled=True):
+    def __init__(self, enabled=True, background=False):
+        """``background``: work nothing on the step's dependency chain waits for soon (parameter gradients, index
+        structures of the backward, weight images): default-priority stream, below the chain's."""
         self.enabled = bool(enabled) and ENABLED
         self._keep = []
         self._dirty = False
@@ -88,7 +100,7 @@ class Branch:
         self._parent = getattr(_tls, "branch", None)     # created inside another branch: nested fork
         if self.enabled:
             self.main = effective_stream()
-            self.side = _next_side(self.main.device, avoid=self.main)
+            self.side = _next_side(self.main.device, avoid=self.main, background=background)
 
     def __call__(self, *tensors):
         self._args = tensors

@@ -225,6 +225,13 @@ int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const float* A, int6
 size_t gn_tc_gemm_rel_workspace_bytes(int32_t M, int32_t n_rel, int32_t f, int32_t K);
 int gn_tc_gemm_rel(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
                    const float* W, float* Y, int64_t ldy, void* ws, size_t ws_bytes, void* stream);
+/* The two halves of gn_tc_gemm_rel: the image depends on W only, so a training step builds it up front, off its
+ * dependency chain (gn_tc_rel_image, `ws` of gn_tc_gemm_rel_workspace_bytes for the SAME M), and the product then
+ * runs with the prepared image (gn_tc_gemm_rel_image). */
+int gn_tc_rel_image(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* W, void* ws, size_t ws_bytes,
+                    void* stream);
+int gn_tc_gemm_rel_image(int32_t M, int32_t n_rel, int32_t f, int32_t K, const float* X, int64_t ldx,
+                         const void* image, size_t image_bytes, float* Y, int64_t ldy, void* stream);
 
 /* Weight-gradient products on the tensor cores: C[Mo, No] = A^T B with A [n, Mo], B [n, No] (features contiguous,
  * the reduction runs over the n node rows): dW = H_{l-1}^T dY of a GCN layer (autograd of gripnet/layers.py:73)
