@@ -20,7 +20,7 @@ namespace gn {
 constexpr int kBK = 16;         // default k-tile depth
 constexpr int kGemmThreads = 256;
 constexpr int kTargetCtas = 148 * 2;
-constexpr int kMaxSplits = 128;
+constexpr int kMaxSplits = 3 * 148;
 
 struct GemmParams {
   int M, N, K;
@@ -67,8 +67,10 @@ static GemmPlan make_plan(int M, int N, int K, int batch, int batch_reduce, int 
   const int64_t tiles = ceil_div(M, pl.bm) * ceil_div(N, pl.bn) * pl.batch_indep;
   int splits = 1;
   if (allow_split && pl.iters >= 4 && tiles < kTargetCtas) {
-    int64_t want = kTargetCtas / tiles;
-    int64_t cap = pl.iters / 2;                      // at least two k-tiles per slice
+    int64_t want = (pl.bk >= 64 ? 3 * 148 : kTargetCtas) / tiles;
+    // at least two 16-deep k-tiles per slice; ONE 64-deep tile is enough (weight gradients: 19 081 rows over
+    // ~296 CTAs of one tile each instead of 100 CTAs of three — the kernel is latency-bound, not bandwidth-bound)
+    int64_t cap = pl.bk >= 64 ? pl.iters : pl.iters / 2;
     splits = int(want < cap ? want : cap);
     if (splits > kMaxSplits) splits = kMaxSplits;
     if (splits < 1) splits = 1;
@@ -296,7 +298,10 @@ extern "C" int gn_sgemm(int transA, int transB, int32_t M, int32_t N, int32_t K,
   else GN_CHECK((launch_cfg<true, true>(pl, p, grid, st)));
   if (pl.splits > 1) {
     const int64_t total = int64_t(M) * N * pl.batch_indep;
-    if (pl.splits >= 16) {
+    // a warp per output (lane = slice) only pays when there are few outputs and many slices (weight gradients:
+    // 32 x 16 outputs, ~100 slices); with many outputs a thread per output reads every slice COALESCED across the
+    // warp (the relation-reduced dX of the RGCN: 645 x 48 outputs, 16 slices — 11.6 -> ~3 us on the backward's chain)
+    if (pl.splits >= 16 && total <= 8192) {
       GN_LAUNCH(splitk_reduce_kernel<32>, (unsigned)ceil_div(total * 32, 256), 256, 0, st, p, pl.batch_indep);
     } else {
       GN_LAUNCH(splitk_reduce_kernel<1>, (unsigned)ceil_div(total, 256), 256, 0, st, p, pl.batch_indep);

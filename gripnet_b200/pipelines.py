@@ -62,26 +62,30 @@ class PoseModel(Module):
             n_dec = dctx.world * dctx.block(data["n_d_global"])
             rel_lo, rel_n = data["dd_rel_lo"], data["dd_rel_n"]
         # the decoder backward's (node, relation) structures depend on the edge lists only — the negatives' one is
-        # rebuilt every step (GripNet-pose.py:131 resamples them) — and the relational layer's W[r] / tensor-core
-        # image on the parameters only.  Both are forked BEFORE the first kernel of the step, on background-priority
-        # streams: they are roots of the captured graph, fill SM slots the dependency chain leaves idle, and are
-        # joined where they are consumed (the decoder's backward; RgcnStack.forward).  PREP_AT = "first" forks them
-        # behind the first supervertex instead (the chain alone starts the step; they then end ~100 us later).
+        # rebuilt every step (GripNet-pose.py:131 resamples them).  The build is forked BEFORE the first kernel of the
+        # step on a background-priority stream: its ~15 small kernels are roots of the captured graph, fill SM slots
+        # the dependency chain leaves idle, and are joined where they are consumed (the decoder's backward).
+        # PREP_AT = "first" forks it behind the first supervertex instead: the chain alone starts the step, but the
+        # build then ends ~30 us after the loss is ready and the backward waits for it (profiles/r02_v19_*).
         prep = streams.Branch(background=PREP_AT == "top")
 
         def fork_prep():
-            if PROLOGUE:
-                self.dd.prologue(n_dec)
             if torch.is_grad_enabled():
                 with prep(pos, neg, et):
                     G.pair_struct(neg, et, n_dec, self.dmt.num_et if dctx is None else rel_n)
                     G.pair_struct(pos, et, n_dec, self.dmt.num_et if dctx is None else rel_n)
 
+        def after_first():
+            # W[r] / image of the relational layer: needed ~30 us after the first supervertex, so they are forked
+            # behind it (two fewer launches ahead of the chain's first kernel)
+            if PROLOGUE:
+                self.dd.prologue(n_dec)
+            if PREP_AT != "top":
+                fork_prep()
+
         if PREP_AT == "top":
             fork_prep()
-            z = self.embed(data)
-        else:
-            z = self.embed(data, after_first=fork_prep)
+        z = self.embed(data, after_first=after_first)
         # `prep` is NOT joined here: only the decoder's backward reads the structures (it joins the branch)
         if dctx is None:
             pos_score, neg_score = self.dmt.score_pair(z, pos, neg, et, struct_branch=prep)
