@@ -22,6 +22,7 @@
 namespace gn {
 
 constexpr int kMaxPeers = 8;
+constexpr int64_t kMulticastMaxSlotBytes = int64_t(4) << 20;
 
 struct PeerArgs {
   char* buf[kMaxPeers];                  // every rank's gather buffer (peer-mapped device pointers)
@@ -115,15 +116,33 @@ __global__ void __launch_bounds__(256) peer_allgather_kernel(const PeerArgs a) {
   const int64_t slot_off = int64_t(a.rank) * a.slot_bytes;
   const int4* __restrict__ src = reinterpret_cast<const int4*>(a.buf[a.rank] + slot_off);
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
-    const int4 v = src[i];
-    if (a.mc != nullptr) {                 // NVLS: one store leaves the GPU, the switch replicates it
-      multimem_st16(a.mc + slot_off + i * 16, v);
-    } else {
+  // NVLS multicast for SMALL slots only (latency-bound: one store instruction instead of world-1).  The switch also
+  // delivers a multicast store back to the sender, so a rank RECEIVES world slots instead of world-1: for large
+  // slots the exchange is ingress-bound and unicast stores win — at world 2 by 2x (profiles/r02_v22_scaled_n2_*:
+  // 512 MB slots moved at 353 GB/s of egress = 706 GB/s of ingress through the multicast mapping)
+  const bool mc_data = a.mc != nullptr && (a.world > 2 && a.slot_bytes <= kMulticastMaxSlotBytes);
+  if (mc_data) {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride)
+      multimem_st16(a.mc + slot_off + i * 16, src[i]);   // NVLS: one store leaves the GPU, the switch replicates it
+  } else {
+    // unicast: four independent 128-bit loads per thread in flight, then the remote stores (peers visited in a
+    // rank-staggered order so the ranks do not all write into the same GPU at once)
+    constexpr int kU = 4;
+    for (int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i0 < n16; i0 += stride * kU) {
+      int4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < n16) v[u] = src[i];
+      }
 #pragma unroll 1
       for (int s = 1; s < a.world; ++s) {
-        const int peer = (a.rank + s) % a.world;
-        reinterpret_cast<int4*>(a.buf[peer] + slot_off)[i] = v;
+        int4* dst = reinterpret_cast<int4*>(a.buf[(a.rank + s) % a.world] + slot_off);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int64_t i = i0 + u * stride;
+          if (i < n16) dst[i] = v[u];
+        }
       }
     }
   }
