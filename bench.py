@@ -379,9 +379,9 @@ def build_pose(args, world, rank, dev, dctx, workload="pose"):
         w = torch.randn(R, D, device=dev)
         coef = torch.randn(E, device=dev)
         ps = pair_struct(pos, et, n_z, R)
-        probes.append(("distmult_fwd_kernel (DistMult scores, one edge list)", 2, E * (24 + 8 * D + 4),
+        probes.append(("distmult_fwd_batch_kernel (DistMult scores, one edge list)", 2, E * (24 + 8 * D + 4),
                        lambda: ops._distmult_fwd(z, w, pos, et, True)))
-        probes.append(("pair_walk_kernel (DistMult backward, one gather pass per edge list)", 2,
+        probes.append(("pair_walk_batch_kernel (DistMult backward, one gather pass per edge list)", 2,
                        2 * E * (8 + 4 + 4 * D) + n_z * R * 4 * D,
                        lambda: ops._pair_walk(ps, coef, z)))
         return probes
@@ -599,9 +599,9 @@ def time_workload(args, workload, world, rank, dev, dctx, steps, flush, with_e2e
             for host, src in zip(io["out_host"], outs):
                 host.copy_(src, non_blocking=True)
 
-        # double-buffered copies at N = 1 (measured and checked there); N > 1 keeps the serial loop unless forced:
-        # a rank that rejects the pipelined run alone would leave the others inside the step's exchanges
-        e2e_want = os.environ.get("GRIPNET_BENCH_E2E", "pipelined" if world == 1 else "serial")
+        # double-buffered copies on every rank; the ranks AGREE on the outcome (MIN over ranks of the per-rank
+        # check below), so either all of them keep the pipelined number or all of them time the serial loop
+        e2e_want = os.environ.get("GRIPNET_BENCH_E2E", "pipelined")
         if e2e_want == "pipelined" and not args.eager:
             good, detail = 1, ""
             try:
@@ -619,7 +619,14 @@ def time_workload(args, workload, world, rank, dev, dctx, steps, flush, with_e2e
                 good, detail = 0, f"{type(e).__name__}: {e}"
                 torch.cuda.synchronize()
             if good != 1:
-                sys.stderr.write(f"bench.py: pipelined e2e rejected on rank {rank} ({detail}); timing the serial loop\n")
+                sys.stderr.write(f"bench.py: pipelined e2e rejected on rank {rank} ({detail})\n")
+            if world > 1:
+                agree = torch.tensor([good], device=dev, dtype=torch.int32)
+                dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+                good = int(agree.item())
+            if good != 1:
+                if rank == 0:
+                    sys.stderr.write("bench.py: timing the serial end-to-end loop instead\n")
                 e2e_ms = None
             barrier()
         if e2e_ms is None:

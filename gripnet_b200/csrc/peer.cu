@@ -242,10 +242,38 @@ __global__ void __launch_bounds__(256) peer_halo_push_kernel(const PeerArgs a, c
     const int32_t* __restrict__ idx = h.idx[peer];
     const int64_t cnt = h.count[peer];
     float4* __restrict__ dst = reinterpret_cast<float4*>(a.buf[peer]) + h.dst_row[peer] * h.row_f4;
-    for (int64_t j = int64_t(blockIdx.x) * rows_per_cta + sub; j < cnt; j += int64_t(gridDim.x) * rows_per_cta) {
-      if (sub >= rows_per_cta) break;
-      const float4* __restrict__ srow = reinterpret_cast<const float4*>(h.src) + int64_t(__ldg(idx + j)) * h.row_f4;
-      for (int c = l; c < h.row_f4; c += lanes) dst[j * h.row_f4 + c] = srow[c];
+    // kHU rows per thread group in flight: index loads, then the row loads, then the remote stores (one dependent
+    // index -> row -> store chain per thread keeps only ~1 MB in flight per GPU, short of the NVLink latency-bandwidth
+    // product)
+    constexpr int kHU = 4;
+    const int64_t step = int64_t(gridDim.x) * rows_per_cta;
+    if (sub >= rows_per_cta) continue;
+    for (int64_t j0 = int64_t(blockIdx.x) * rows_per_cta + sub; j0 < cnt; j0 += step * kHU) {
+      int32_t r[kHU];
+#pragma unroll
+      for (int u = 0; u < kHU; ++u) {
+        const int64_t j = j0 + u * step;
+        r[u] = j < cnt ? __ldg(idx + j) : 0;
+      }
+      if (h.row_f4 <= 32) {                      // one float4 per lane and row (rows of up to 128 floats)
+        float4 v[kHU];
+#pragma unroll
+        for (int u = 0; u < kHU; ++u)
+          if (l < h.row_f4) v[u] = __ldg(reinterpret_cast<const float4*>(h.src) + int64_t(r[u]) * h.row_f4 + l);
+#pragma unroll
+        for (int u = 0; u < kHU; ++u) {
+          const int64_t j = j0 + u * step;
+          if (j < cnt && l < h.row_f4) dst[j * h.row_f4 + l] = v[u];
+        }
+      } else {
+#pragma unroll 1
+        for (int u = 0; u < kHU; ++u) {
+          const int64_t j = j0 + u * step;
+          if (j >= cnt) break;
+          const float4* __restrict__ srow = reinterpret_cast<const float4*>(h.src) + int64_t(r[u]) * h.row_f4;
+          for (int c = l; c < h.row_f4; c += lanes) dst[j * h.row_f4 + c] = srow[c];
+        }
+      }
     }
   }
   signal_and_wait(a);

@@ -104,7 +104,13 @@ __global__ void __launch_bounds__(256) b_image_kernel(const BView bv, int K, int
 // ---------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
+// PF = k-blocks of A a loader thread keeps in flight beyond the one it is converting.  One CTA per SM (large
+// operands: three A stages + resident B) streams A from HBM with only its own loads in flight, and ncu showed it
+// latency-bound at ~25 % of the HBM peak with PF = 1 (profiles/r02_v17_ncu_full_{aminer,freebase-d}.csv:
+// 16 KB per SM and round trip); PF = 3 keeps 64 KB per SM in flight, also across the epilogue of a tile.  Two CTAs
+// per SM keep PF = 1 (register budget of 102 per thread).
+template <int PF>
+__global__ void __launch_bounds__(kThreads, PF == 1 ? 2 : 1) tc_gemm_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[3], empty_bar[3], acc_bar, acc_free, b_ready;
   __shared__ uint32_t tmem_base_slot;
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
     // =============================== A loaders ===============================
     const int c = threadIdx.x & 7;           // k-chunk of this thread
     const int r_base = threadIdx.x >> 3;     // rows r_base + 32*i
-    float4 cur[4], nxt[4];
+    float4 q[PF + 1][4];                     // q[0]: the k-block being converted, q[d]: d k-blocks ahead
     auto issue = [&](int m0, int kb, float4(&dst)[4]) {
       const int k = kb * BK + c * 4;
 #pragma unroll
@@ -160,27 +166,36 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
         else dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    // k-block `itx` of this CTA's flattened (tile, k-block) sequence; runs ahead across tile boundaries, so the
+    // next tiles' loads are in flight during the epilogue of the current one
+    const int total_it = my_tiles * p.n_kb;
+    auto issue_it = [&](int itx, float4(&dst)[4]) {
+      if (itx < total_it) {
+        const int tt = itx / p.n_kb;
+        issue((int(blockIdx.x) + tt * int(gridDim.x)) * BM, itx - tt * p.n_kb, dst);
+      }
+    };
     const int quarter = warp & 3;                      // TMEM lanes 32*quarter .. +31
     const int halves = (warp >> 2);                    // 0: low column half, 1: high column half
     const int n_tile0 = tile_n * nt;
     const int groups = nt / 16;                        // 16-column groups in this tile
     const int g_begin = halves * ((groups + 1) / 2);
     const int g_end = halves ? groups : (groups + 1) / 2;
-    if (my_tiles > 0) issue(int(blockIdx.x) * BM, 0, cur);
+#pragma unroll
+    for (int d = 0; d < PF; ++d) issue_it(d, q[d]);
     for (int t = 0; t < my_tiles; ++t) {
       const int m0 = (int(blockIdx.x) + t * int(gridDim.x)) * BM;
       for (int kb = 0; kb < p.n_kb; ++kb) {
         const int it = t * p.n_kb + kb;
         const int s = it % S, use = it / S;
-        if (kb + 1 < p.n_kb) issue(m0, kb + 1, nxt);
-        else if (t + 1 < my_tiles) issue(m0 + int(gridDim.x) * BM, 0, nxt);   // next tile: in flight during the epilogue
+        issue_it(it + PF, q[PF]);
         if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
         unsigned char* a_hi = smem + s * stage_sz;
         unsigned char* a_lo = a_hi + part_bytes(BM);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           float4 hi, lo;
-          split4(cur[i], hi, lo);
+          split4(q[0][i], hi, lo);
           const int off = c * plane_bytes(BM) + (r_base + 32 * i) * 16;
           *reinterpret_cast<float4*>(a_hi + off) = hi;
           *reinterpret_cast<float4*>(a_lo + off) = lo;
@@ -188,7 +203,9 @@ __global__ void __launch_bounds__(kThreads, 2) tc_gemm_kernel(const Params p) {
         fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core
         mbar_arrive(&full_bar[s]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+        for (int d = 0; d < PF; ++d)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) q[d][i] = q[d + 1][i];
       }
       // =============================== epilogue of tile t ================================
       mbar_wait(&acc_bar, t & 1);
@@ -436,11 +453,16 @@ static int tc_set_smem_attr() {
   static std::atomic<int> attr_set{0};
   if (!attr_set.load(std::memory_order_acquire)) {
     cudaError_t e =
-        cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(tc::tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::tc_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::tc_gemm_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
     // the products are HBM-bound streams of A: two CTAs per SM (smem <= 99 KB and <= 256 TMEM columns each for the
     // layer transforms) double the loads in flight, so ask for the largest shared-memory carveout
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc::tc_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+      e = cudaFuncSetAttribute(tc::tc_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) {
       (void)cudaGetLastError();
@@ -454,12 +476,33 @@ static int tc_set_smem_attr() {
 
 // CTAs along M: persistent over the M tiles — as many CTAs as can be resident (two per SM when shared memory and
 // TMEM allow it), each walking its tiles with a stride of the grid
+// GRIPNET_B200_TC_PREFETCH=1 keeps the shallow loader everywhere (A/B measurements)
+static bool tc_shallow_only() {
+  const char* e = std::getenv("GRIPNET_B200_TC_PREFETCH");
+  return e && e[0] == '1';
+}
+
+static int tc_ctas_per_sm(const tc::Plan& pl) {
+  return (2 * pl.smem_bytes <= 220 * 1024 && 2 * pl.tmem_cols <= 512) ? 2 : 1;
+}
+
 static unsigned tc_grid_x(int M, const tc::Plan& pl) {
   const int64_t m_tiles = ceil_div(M, tc::BM);
-  const int per_sm = (2 * pl.smem_bytes <= 220 * 1024 && 2 * pl.tmem_cols <= 512) ? 2 : 1;
+  const int per_sm = tc_ctas_per_sm(pl);
   int64_t resident = int64_t(148) * per_sm / pl.n_tiles;
   if (resident < 1) resident = 1;
   return unsigned(m_tiles < resident ? m_tiles : resident);
+}
+
+// deep prefetch when one CTA owns an SM and walks several M tiles (a long stream of A); PF = 1 otherwise
+static int tc_launch(const tc::Plan& pl, int M, dim3 grid, const tc::Params& p, cudaStream_t st) {
+  const bool deep = tc_ctas_per_sm(pl) == 1 && ceil_div(M, tc::BM) > int64_t(grid.x) && !tc_shallow_only();
+  if (deep) {
+    GN_LAUNCH(tc::tc_gemm_kernel<3>, grid, tc::kThreads, pl.smem_bytes, st, p);
+  } else {
+    GN_LAUNCH(tc::tc_gemm_kernel<1>, grid, tc::kThreads, pl.smem_bytes, st, p);
+  }
+  return GN_OK;
 }
 
 // B small enough for the B-producer warp to split it inside the main kernel (one N tile, <= 16 float4 per lane
@@ -502,7 +545,7 @@ extern "C" int gn_tc_gemm(int transB, int32_t M, int32_t N, int32_t K, const flo
   p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc; p.b_resident = pl.b_resident;
   GN_CHECK(tc_set_smem_attr());
   dim3 grid(tc_grid_x(M, pl), (unsigned)pl.n_tiles);
-  GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, st, p);
+  GN_CHECK(tc_launch(pl, M, grid, p, st));
   return GN_OK;
 }
 
@@ -570,7 +613,7 @@ extern "C" int gn_tc_gemm_rel_image(int32_t M, int32_t n_rel, int32_t f, int32_t
   p.n_acc = pl.n_acc; p.kb_per_acc = pl.kb_per_acc; p.b_resident = pl.b_resident;
   GN_CHECK(tc_set_smem_attr());
   dim3 grid(tc_grid_x(M, pl), (unsigned)pl.n_tiles);
-  GN_LAUNCH(tc::tc_gemm_kernel, grid, tc::kThreads, pl.smem_bytes, as_stream(stream), p);
+  GN_CHECK(tc_launch(pl, M, grid, p, as_stream(stream)));
   return GN_OK;
 }
 

@@ -33,7 +33,9 @@ def _tc(tb, A, B, C, addend=None, mask=None):
 
 @pytest.mark.parametrize("tb", [0, 1])
 @pytest.mark.parametrize("m,n,k", [(128, 16, 8), (300, 16, 32), (1000, 64, 128), (4173, 128, 256), (513, 48, 48),
-                                   (2000, 512, 128), (777, 272, 80), (130, 20, 4), (5000, 32, 512), (64, 256, 36), (3000, 128, 1024), (1500, 256, 640)])
+                                   (2000, 512, 128), (777, 272, 80), (130, 20, 4), (5000, 32, 512), (64, 256, 36), (3000, 128, 1024), (1500, 256, 640),
+                                   # one CTA per SM walking several M tiles: the deep-prefetch loader (tc_gemm_kernel<3>)
+                                   (40000, 128, 256), (25003, 256, 64), (60000, 64, 288)])
 def test_tc_gemm_matches_float64(tb, m, n, k):
     rs = np.random.RandomState(m + n + k)
     A = rs.randn(m, k).astype(np.float32)
