@@ -14,6 +14,8 @@
 // Node classification — replaces torch.argmax + gripnet/utils.py:38-46 (micro_macro: sklearn f1_score
 // micro / macro) and :49-52 (acc): one pass builds the C x C confusion matrix with integer atomics
 // (order-independent), a single block turns it into micro-F1, macro-F1 and accuracy.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace gn {
@@ -50,94 +52,135 @@ __global__ void gather_i32_kernel(const int32_t* __restrict__ src, const int32_t
   if (i < n) dst[i] = src[idx[i]];
 }
 
-constexpr int kMtThreads = 1024;   // one CTA walks a relation's ranked slice: wide tiles keep the walk short
+constexpr int kMtThreads = 1024;   // wide tiles keep the walk of a ranked slice short
 constexpr int kMtItems = 8;
 constexpr int kMtTile = kMtThreads * kMtItems;
+constexpr int kMtCluster = 8;      // CTAs (one thread-block cluster) per relation
 
-struct ScanPair {
-  int sum;     // positives
-  int last;    // last threshold-end position (relative to the slice), -1 = none
+// Running aggregate of a prefix of a relation's ranked slice: positives so far, the last threshold-end position
+// (relative to the slice, -1 = none) and the positives up to and including that position.
+struct ScanTriple {
+  int sum, last, tp_last;
 };
 
-__device__ __forceinline__ ScanPair combine(const ScanPair a, const ScanPair b) {   // a precedes b
-  return ScanPair{a.sum + b.sum, max(a.last, b.last)};
+__device__ __forceinline__ ScanTriple combine(const ScanTriple a, const ScanTriple b) {   // a precedes b
+  ScanTriple r;
+  r.sum = a.sum + b.sum;
+  if (b.last >= 0) { r.last = b.last; r.tp_last = a.sum + b.tp_last; }
+  else { r.last = a.last; r.tp_last = a.tp_last; }
+  return r;
 }
 
-__global__ void __launch_bounds__(kMtThreads, 1) lp_metrics_kernel(const float* __restrict__ pos, int64_t n_pos,
-                                                                const float* __restrict__ neg,
-                                                                const int32_t* __restrict__ perm,
-                                                                const int32_t* __restrict__ rowptr,
-                                                                int32_t* __restrict__ tpcum, int n_rel,
-                                                                double* __restrict__ record) {
-  const int r = blockIdx.x;
+__device__ __forceinline__ ScanTriple shfl_up(const ScanTriple v, int d) {
+  return ScanTriple{__shfl_up_sync(kFull, v.sum, d), __shfl_up_sync(kFull, v.last, d),
+                    __shfl_up_sync(kFull, v.tp_last, d)};
+}
+
+// One thread-block CLUSTER of kMtCluster CTAs per relation (round 1: one CTA per relation — 16 CTAs on 148 SMs at
+// pose-0 size, 94 us, the tail of the training epoch).  CTA `rank` owns the rank-th contiguous part of the
+// relation's ranked slice:
+//   pass 1  aggregate of the part (positives, last threshold end, positives at that end) -> shared memory;
+//   cluster barrier; the carry of a part = the aggregates of the parts before it, read over distributed shared memory;
+//   pass 2  the trapezoid / step sums of the part's threshold ends, starting from the carry (a part of one tile
+//           keeps its items in registers between the passes);
+//   cluster barrier; CTA 0 adds the kMtCluster partial sums in part order and writes the record.
+// Counts are exact integers; the float64 sums have a fixed order (thread items, shuffle tree, warps, parts).
+__global__ void __cluster_dims__(kMtCluster, 1, 1) __launch_bounds__(kMtThreads, 1)
+    lp_metrics_kernel(const float* __restrict__ pos, int64_t n_pos, const float* __restrict__ neg,
+                      const int32_t* __restrict__ perm, const int32_t* __restrict__ rowptr, int n_rel,
+                      double* __restrict__ record) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int r = int(blockIdx.x) / kMtCluster;
+  const int rank = int(cluster.block_rank());
   const int beg = rowptr[r], end = rowptr[r + 1];
   const int len = end - beg;
+  const int part = (len + kMtCluster - 1) / kMtCluster;
+  const int c0 = min(len, rank * part), c1 = min(len, c0 + part);      // this CTA's positions [c0, c1)
+  const int n_tiles = (c1 - c0 + kMtTile - 1) / kMtTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  __shared__ ScanPair s_warp[kMtThreads / 32];
-  __shared__ ScanPair s_carry;
-  __shared__ double s_red[3][kMtThreads / 32];
+  __shared__ ScanTriple s_warp[kMtThreads / 32];
+  __shared__ ScanTriple s_total;           // running aggregate (carry + tiles so far) of the current pass
+  __shared__ ScanTriple s_agg;             // pass-1 aggregate of this part: read by the other CTAs of the cluster
+  __shared__ double s_red[2][kMtThreads / 32];
   __shared__ long long s_roc[kMtThreads / 32];
-  if (threadIdx.x == 0) s_carry = ScanPair{0, -1};
-  __syncthreads();
+  __shared__ double s_part[2];             // this part's (ap, prc): read by CTA 0 of the cluster
+  __shared__ long long s_part_roc;
 
   auto score_at = [&](int i) -> float {
     const int idx = perm[i];
     return idx < n_pos ? pos[idx] : neg[idx - n_pos];
   };
 
-  long long roc = 0;          // sum (fp_k - fp_{k-1}) (tp_k + tp_{k-1}); <= 2 P N < 2^63
-  double ap = 0.0, prc = 0.0;
-  for (int base = 0; base < len; base += kMtTile) {
-    const int j0 = base + threadIdx.x * kMtItems;         // relative position of this thread's first item
+  int lab[kMtItems];
+  bool bnd[kMtItems];
+  ScanTriple mine;
+  // items [j0, j0 + kMtItems) of the slice: labels, threshold ends, the thread's own aggregate
+  auto load_tile = [&](int j0) {
     float sc[kMtItems + 1];
-    int lab[kMtItems];
-    bool bnd[kMtItems];
 #pragma unroll
-    for (int q = 0; q <= kMtItems; ++q) sc[q] = (j0 + q < len) ? score_at(beg + j0 + q) : 0.f;
-    ScanPair mine{0, -1};
+    for (int q = 0; q <= kMtItems; ++q) sc[q] = (j0 + q < len && j0 + q <= c1) ? score_at(beg + j0 + q) : 0.f;
+    mine = ScanTriple{0, -1, 0};
 #pragma unroll
     for (int q = 0; q < kMtItems; ++q) {
       const int j = j0 + q;
-      const bool valid = j < len;
+      const bool valid = j < c1;
       lab[q] = (valid && perm[beg + j] < n_pos) ? 1 : 0;
       bnd[q] = valid && (j + 1 == len || sc[q + 1] != sc[q]);
       mine.sum += lab[q];
-      if (bnd[q]) mine.last = j;
+      if (bnd[q]) { mine.last = j; mine.tp_last = mine.sum; }
     }
-    // block-exclusive scan of (sum, last): warp shuffles, then the warp totals
-    ScanPair inc = mine;
+  };
+  // exclusive prefix of `mine` over the CTA, on top of `carry`; s_total <- carry + the whole tile
+  auto scan_tile = [&](const ScanTriple carry) -> ScanTriple {
+    ScanTriple inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int os = __shfl_up_sync(kFull, inc.sum, d);
-      const int ol = __shfl_up_sync(kFull, inc.last, d);
-      if (lane >= d) inc = combine(ScanPair{os, ol}, inc);
+      const ScanTriple o = shfl_up(inc, d);
+      if (lane >= d) inc = combine(o, inc);
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    ScanPair pre = s_carry;
+    ScanTriple pre = carry;
     for (int w = 0; w < warp; ++w) pre = combine(pre, s_warp[w]);
-    {
-      const int es = __shfl_up_sync(kFull, inc.sum, 1);
-      const int el = __shfl_up_sync(kFull, inc.last, 1);
-      if (lane > 0) pre = combine(pre, ScanPair{es, el});
-    }
-    // inclusive positive counts of this thread's items
+    const ScanTriple e = shfl_up(inc, 1);
+    if (lane > 0) pre = combine(pre, e);
+    if (threadIdx.x == kMtThreads - 1) s_total = combine(pre, mine);
+    __syncthreads();                                     // s_total visible, s_warp free for the next tile
+    return pre;
+  };
+
+  // ---- pass 1: aggregate of this part
+  ScanTriple carry{0, -1, 0};
+  for (int t = 0; t < n_tiles; ++t) {
+    load_tile(c0 + t * kMtTile + int(threadIdx.x) * kMtItems);
+    (void)scan_tile(carry);
+    carry = s_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s_agg = carry;
+  cluster.sync();
+  ScanTriple cin{0, -1, 0};
+  for (int q = 0; q < rank; ++q) cin = combine(cin, *cluster.map_shared_rank(&s_agg, q));
+
+  // ---- pass 2: sums over this part's threshold ends
+  long long roc = 0;          // sum (fp_k - fp_{k-1}) (tp_k + tp_{k-1}); <= 2 P N < 2^63
+  double ap = 0.0, prc = 0.0;
+  carry = cin;
+  for (int t = 0; t < n_tiles; ++t) {
+    const int j0 = c0 + t * kMtTile + int(threadIdx.x) * kMtItems;
+    if (n_tiles > 1) load_tile(j0);                      // a single tile is still in registers
+    const ScanTriple pre = scan_tile(carry);
+    carry = s_total;
     int tp = pre.sum;
-    int tps[kMtItems];
+    int prev = pre.last;
+    long long tp_p = pre.last >= 0 ? pre.tp_last : 0;
 #pragma unroll
     for (int q = 0; q < kMtItems; ++q) {
       tp += lab[q];
-      tps[q] = tp;
-      if (j0 + q < len) tpcum[beg + j0 + q] = tp;
-    }
-    __syncthreads();                                      // tpcum of this tile (and s_warp reads) complete
-    int prev = pre.last;
-#pragma unroll
-    for (int q = 0; q < kMtItems; ++q) {
       if (!bnd[q]) continue;
       const int j = j0 + q;
-      const long long tp_k = tps[q], fp_k = (long long)(j + 1) - tp_k;
-      const long long tp_p = prev >= 0 ? tpcum[beg + prev] : 0;
+      const long long tp_k = tp, fp_k = (long long)(j + 1) - tp_k;
       const long long fp_p = (long long)(prev + 1) - tp_p;
       roc += (fp_k - fp_p) * (tp_k + tp_p);
       const double prec_k = double(tp_k) / double(tp_k + fp_k);
@@ -146,8 +189,8 @@ __global__ void __launch_bounds__(kMtThreads, 1) lp_metrics_kernel(const float* 
       ap += d_tp * prec_k;
       prc += d_tp * (prec_k + prec_p) * 0.5;
       prev = j;
+      tp_p = tp_k;
     }
-    if (threadIdx.x == kMtThreads - 1) s_carry = combine(pre, mine);
     __syncthreads();
   }
   // fixed-order block reduction
@@ -171,12 +214,28 @@ __global__ void __launch_bounds__(kMtThreads, 1) lp_metrics_kernel(const float* 
       ap_t += s_red[0][w];
       prc_t += s_red[1][w];
     }
-    const double P = double(s_carry.sum), N = double(len) - P;
+    s_part_roc = roc_t;
+    s_part[0] = ap_t;
+    s_part[1] = prc_t;
+  }
+  cluster.sync();
+  if (rank == 0 && threadIdx.x == 0) {
+    long long roc_t = 0;
+    double ap_t = 0.0, prc_t = 0.0;
+    int positives = 0;
+    for (int q = 0; q < kMtCluster; ++q) {
+      roc_t += *cluster.map_shared_rank(&s_part_roc, q);
+      ap_t += cluster.map_shared_rank(s_part, q)[0];
+      prc_t += cluster.map_shared_rank(s_part, q)[1];
+      positives += cluster.map_shared_rank(&s_agg, q)->sum;
+    }
+    const double P = double(positives), N = double(len) - P;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     record[0 * n_rel + r] = P > 0 ? prc_t / P : nan;                         // auprc
     record[1 * n_rel + r] = (P > 0 && N > 0) ? double(roc_t) / (2.0 * P * N) : nan;   // auroc
     record[2 * n_rel + r] = P > 0 ? ap_t / P : nan;                          // ap
   }
+  cluster.sync();            // no CTA leaves while CTA 0 still reads its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -259,7 +318,7 @@ int gn_lp_metrics(const float* pos_score, int64_t n_pos, const float* neg_score,
   cudaStream_t st = as_stream(stream);
   Arena a(ws, ws_bytes);
   const size_t cap = size_t(n > 0 ? n : 1);
-  int32_t* key = a.take<int32_t>(cap);      // rank keys, then the relation keys, then tpcum
+  int32_t* key = a.take<int32_t>(cap);      // rank keys, then the relation keys
   int32_t* rel = a.take<int32_t>(cap);
   int32_t* ksorted = a.take<int32_t>(cap);
   int32_t* perm1 = a.take<int32_t>(cap);
@@ -277,8 +336,8 @@ int gn_lp_metrics(const float* pos_score, int64_t n_pos, const float* neg_score,
     GN_CHECK(sort_pairs(key, perm1, ksorted, perm2, n, bits_for(int64_t(n_rel) + 1), sws, sws_bytes, st));
   }
   GN_CHECK(rowptr_from_sorted(ksorted, n, n_rel + 1, rowptr, st));
-  GN_LAUNCH(lp_metrics_kernel, (unsigned)n_rel, kMtThreads, 0, st, pos_score, n_pos, neg_score,
-            (const int32_t*)perm2, (const int32_t*)rowptr, key, (int)n_rel, record);
+  GN_LAUNCH(lp_metrics_kernel, (unsigned)n_rel * kMtCluster, kMtThreads, 0, st, pos_score, n_pos, neg_score,
+            (const int32_t*)perm2, (const int32_t*)rowptr, (int)n_rel, record);
   return GN_OK;
 }
 

@@ -71,7 +71,7 @@ def _ranges(sizes):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["continuous", "ties", "saturated", "signed"])
-@pytest.mark.parametrize("sizes", [[1], [5, 3, 9], [1025, 1, 4096, 333, 2], [2500] * 16])
+@pytest.mark.parametrize("sizes", [[1], [5, 3, 9], [1025, 1, 4096, 333, 2], [2500] * 16, [40000, 7]])   # last: > 1 tile per CTA
 def test_device_lp_metrics_match_oracle_and_sklearn(kind, sizes):
     from gripnet_b200.metrics import lp_metrics
     rs = np.random.RandomState(len(sizes))
