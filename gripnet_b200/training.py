@@ -9,7 +9,7 @@ backward, Adam, micro / macro F1 of the arg-max predictions).
 """
 import torch
 
-from . import metrics
+from . import metrics, streams
 from .capture import CapturedStep
 from .optim import Adam
 from .utils import NegativeSampler
@@ -82,15 +82,21 @@ class PoseTrainer(_Trainer):
             metrics.lp_metrics(dummy, dummy, self.range_list, out=self.record)
         outs = {}
 
+        # the evaluation record needs the forward's scores only: its kernels (rank keys, two radix sorts, the
+        # per-relation walk) run on a background branch next to the backward pass and Adam, joined at the epoch's end
         def fn():
             self.sampler.sample(out=self.neg_edge_index)
             outs["o"] = model(data, self.neg_edge_index)
+            if with_metrics:
+                _, _, pos_score, neg_score = outs["o"]
+                outs["br"] = streams.Branch(background=True)
+                with outs["br"](pos_score, neg_score):
+                    metrics.lp_metrics(pos_score, neg_score, self.range_list, out=self.record)
             return outs["o"]
 
         def post_extra():
             if with_metrics:
-                _, _, pos_score, neg_score = outs["o"]
-                metrics.lp_metrics(pos_score, neg_score, self.range_list, out=self.record)
+                outs.pop("br").join()
 
         self._capture(fn, model, lr, warmup, post_extra, eager)
         self.sampler.state.zero_()                         # epoch 0 draws the sampler's first negatives
@@ -113,13 +119,17 @@ class NodeTrainer(_Trainer):
 
         def fn():
             outs["o"] = model(data)
+            if with_metrics:                       # needs the forward's scores only: next to the backward pass
+                score = outs["o"][2].detach()
+                outs["br"] = streams.Branch(background=True)
+                with outs["br"](score):
+                    self.pred = metrics.argmax_rows(score)
+                    metrics.nc_metrics(data["train_node_class"], self.pred, n_class, out=self.f1)
             return outs["o"]
 
         def post_extra():
             if with_metrics:
-                score = outs["o"][2].detach()
-                self.pred = metrics.argmax_rows(score)
-                metrics.nc_metrics(data["train_node_class"], self.pred, n_class, out=self.f1)
+                outs.pop("br").join()
 
         self._capture(fn, model, lr, warmup, post_extra, eager)
 
