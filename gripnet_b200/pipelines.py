@@ -273,7 +273,10 @@ def shard_chain_streamed(make_graph, dctx, device):
 
 
 def to_device(data, device):
-    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
+    """Tensors of a graph dict on ``device``, CONTIGUOUS: an edge list that arrives as a strided view (numpy fancy
+    indexing returns Fortran-ordered index arrays) would be re-packed by every decoder call of every step
+    (``r02_final_launches_pose2.csv``: a 133 MB strided copy, 62 us per step at pose-2 size)."""
+    return {k: (v.to(device).contiguous() if torch.is_tensor(v) else v) for k, v in data.items()}
 
 
 def load_flat_params(model, flat):

@@ -217,6 +217,37 @@ def test_distmult_pose_sized_and_pair(n, kernels, monkeypatch):
     assert rel_err(res[1][2], res[0][2]) < 1e-6 and rel_err(res[1][3], res[0][3]) < 1e-6
 
 
+def test_distmult_short_rows_with_hub_rows():
+    """(node, relation) rows that are short on average (the pose-2 regime: ~6 entries here, chunk length 32) with
+    two hub rows split over ~190 chunks each, which finish through the partial / last-arrival path; against
+    float64, and bit-identical run to run."""
+    from gripnet_b200 import ops
+    rs = np.random.RandomState(17)
+    d = _dev()
+    n, D, r, e, hub = 2000, 80, 4, 20000, 6000
+    src = np.r_[rs.randint(0, n, e), np.full(hub, 7)]
+    dst = np.r_[rs.randint(0, n, e), rs.randint(0, n, hub)]
+    et = np.r_[rs.randint(0, r, e), np.full(hub, 1)]
+    order = np.argsort(et, kind="stable")
+    ei = torch.from_numpy(np.stack([src, dst])[:, order].copy())
+    et = torch.from_numpy(et[order].copy())
+    z = torch.randn(n, D, dtype=torch.float64) * 0.3
+    w = torch.randn(r, D, dtype=torch.float64)
+    zr, wr = z.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = torch.sigmoid((zr[ei[0]] * zr[ei[1]] * wr[et]).sum(1))
+    gvec = torch.linspace(-1, 1, ei.size(1), dtype=torch.float64)
+    (ref * gvec).sum().backward()
+    grads = []
+    for _ in range(2):
+        zc, wc = z.float().to(d).requires_grad_(True), w.float().to(d).requires_grad_(True)
+        out = ops.DistMult.apply(zc, wc, ei.to(d), et.to(d), True)
+        (out * gvec.float().to(d)).sum().backward()
+        assert rel_err(out, ref) < TOL
+        assert rel_err(zc.grad, zr.grad) < TOL and rel_err(wc.grad, wr.grad) < TOL
+        grads.append((zc.grad.clone(), wc.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1])
+
+
 def test_distmult_backward_deterministic_and_hub_rows():
     from gripnet_b200 import ops
     rs = np.random.RandomState(3)
