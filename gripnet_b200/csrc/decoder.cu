@@ -83,16 +83,25 @@ __global__ void __launch_bounds__(256, NV <= 3 ? 4 : 3) distmult_fwd_batch_kerne
   const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int64_t n_batches = (n_edges + 31) >> 5;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the indices of this warp's NEXT batch are fetched while the rows of the current one are in flight
+  int s_nxt = 0, d_nxt = 0, r_nxt = 0;
+  if (warp < n_batches && (warp << 5) + lane < n_edges) {
+    s_nxt = int(__ldg(src + (warp << 5) + lane));
+    d_nxt = int(__ldg(dst + (warp << 5) + lane));
+    r_nxt = int(__ldg(etype + (warp << 5) + lane));
+  }
   for (int64_t b = warp; b < n_batches; b += n_warps) {
     const int64_t e = (b << 5) + lane;
     const bool live = e < n_edges;
-    int s = 0, d = 0, r;
-    const int r_first = int(__ldg(etype + (b << 5)));
-    r = r_first;
-    if (live) {
-      s = int(__ldg(src + e));
-      d = int(__ldg(dst + e));
-      r = int(__ldg(etype + e));
+    const int s = s_nxt, d = d_nxt;
+    const int r_first = __shfl_sync(kFull, r_nxt, 0);          // lane 0 of a batch is always a live edge
+    const int r = live ? r_nxt : r_first;
+    s_nxt = d_nxt = r_nxt = 0;
+    const int64_t e2 = ((b + n_warps) << 5) + lane;
+    if (e2 < n_edges) {
+      s_nxt = int(__ldg(src + e2));
+      d_nxt = int(__ldg(dst + e2));
+      r_nxt = int(__ldg(etype + e2));
     }
     const bool uniform = __all_sync(kFull, r == r_first);
     float4 wv[NV];
@@ -614,7 +623,7 @@ int gn_distmult_fwd(const float* z, int64_t ldz, int32_t D, const float* w, cons
   if (v4 && D <= 128 && ldz < (int64_t(1) << 30) && !legacy_decoder_kernels()) {
     const int nv = (D / 4 + 7) / 8;
     int64_t nwarps = ceil_div(n_edges, 32);
-    const int64_t cap = int64_t(148) * 4 * 8 * 2;            // two batches per resident warp before the loop pays off
+    const int64_t cap = int64_t(148) * 4 * 8;                // one wave of resident warps; each walks its batches
     if (nwarps > cap) nwarps = cap;
     const unsigned g = (unsigned)ceil_div(nwarps, 8);
 #define GN_FWDB_CASE(N)                                                                                              \
