@@ -158,6 +158,49 @@ def test_rgcn_variants():
     _check_grads(conv, g)
 
 
+def test_rgcn_prologue_is_bit_identical_and_ignores_stale_parameters():
+    """``homoGraph.prologue`` (W[r] and the tensor-core operand image built ahead, on a background stream) changes
+    where the parameter-only work runs, not its result: outputs and gradients are bit-identical with and without it;
+    a prologue taken BEFORE an in-place parameter update is discarded (version check), not used."""
+    import gripnet_b200 as gb
+    from gripnet_b200 import ops
+    v = load_grouped("variants")
+    c = v["rgcn2"]
+    p, _ = _split(c)
+    m = gb.homoGraph([12, 20, 8], multi_relational=True, n_rela=4, n_base=6)
+    m.load_state_dict(p)
+    m = m.to(_dev())
+    args = (c["edge_index"].to(_dev()),)
+    kw = dict(edge_type=c["edge_type"].to(_dev()), range_list=c["range_list"].to(_dev()), if_catout=True)
+
+    def run(prologue):
+        for q in m.parameters():
+            q.grad = None
+        x = c["x"].to(_dev()).requires_grad_(True)
+        if prologue:
+            assert m.prologue(x.size(0)) is not None
+            assert len(ops.RelPrologue._pending) == 2           # one entry per relational layer
+        out = m(x, *args, **kw)
+        assert len(ops.RelPrologue._pending) == 0               # taken by the forward
+        (out * _w(out)).sum().backward()
+        torch.cuda.synchronize()
+        return [out.detach().clone(), x.grad.clone()] + [q.grad.clone() for q in m.parameters()]
+
+    plain, ahead = run(False), run(True)
+    for a, b in zip(plain, ahead):
+        assert torch.equal(a, b)
+    assert rel_err(ahead[0], c["out"]) < TOL
+    # stale prologue: parameters rewritten in place after it was taken
+    m.prologue(c["x"].size(0))
+    with torch.no_grad():
+        for conv in m.conv_list:
+            conv.att.mul_(2.0)
+    x = c["x"].to(_dev())
+    stale = m(x, *args, **kw)
+    fresh = m(x, *args, **kw)
+    assert torch.equal(stale, fresh) and not torch.equal(stale.detach(), ahead[0])
+
+
 def test_gcn_improved_uncached_and_norm_api():
     import gripnet_b200 as gb
     c = load_grouped("variants")["gcn_improved"]
