@@ -21,8 +21,16 @@ the stream that allocated it):
 * results are allocated by the caller (on its stream) and must not be consumed before ``join()``.
 
 Branches nest (a branch created inside ``with other:`` forks off that side stream and hands its
-temporaries to the parent on ``join``).  Partitioned (multi-GPU) runs do not branch: their
-collectives are issued on the caller's stream.
+temporaries to the parent on ``join``).  No collective / peer exchange is ever issued inside a branch: a
+partitioned (multi-GPU) run branches only for work that stays on the GPU (parameter gradients when their reduction
+is deferred to the end of the step, index structures, weight images).
+
+A branch may be joined by its CONSUMER instead of where it was forked: ``pipelines.PoseModel`` forks the build of
+the decoder backward's index structures before the first kernel of a step and hands the branch to
+``ops.DistMultPair``, whose backward joins it; ``ops.RelPrologue`` does the same for the relational layer's
+parameter-only work.  A branch that is dropped un-joined joins itself first (``__del__``), so the temporaries it
+holds are never released under running side work.  ``background=True`` puts a branch on a default-priority stream,
+below the high-priority stream the step's dependency chain is captured on (``capture.CapturedStep``).
 """
 import os
 import threading
