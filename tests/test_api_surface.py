@@ -108,3 +108,25 @@ def test_modules_copy_and_pickle_without_their_native_graph_handles():
     h.conv_list[0]._graph = object()
     h2 = copy.deepcopy(h)
     assert h2.conv_list[0]._graph is None and sorted(h2.state_dict()) == sorted(h.state_dict())
+
+
+def test_every_environment_switch_is_documented():
+    """Each ``GRIPNET_B200_*`` / ``GRIPNET_BENCH_*`` variable read anywhere in the package, the kernels or bench.py is
+    listed in README.md's table of A/B switches (the table uses ``_SUFFIX`` shorthand for variables that share a
+    prefix)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    found = set()
+    for base, _, files in os.walk(os.path.join(root, "gripnet_b200")):
+        if os.sep + "build" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                found |= set(re.findall(r'"(GRIPNET_B(?:200|ENCH)_[A-Z0-9_]+)"', open(os.path.join(base, f)).read()))
+    found |= set(re.findall(r'"(GRIPNET_B(?:200|ENCH)_[A-Z0-9_]+)"', open(os.path.join(root, "bench.py")).read()))
+    readme = open(os.path.join(root, "README.md")).read()
+    assert found, "no switches found: the scan is broken"
+    for name in sorted(found):
+        suffix = name.replace("GRIPNET_B200", "")
+        assert name in readme or ("`" + suffix + "`") in readme, f"{name} is not documented in README.md"
